@@ -1,0 +1,908 @@
+// libastre_gpu.so -- context, device mirror and the C ABI of include/astre_gpu.h.
+// sm_100a only; there is no CPU path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/astre_gpu.h"
+#include "host_math.hpp"
+#include "kernels_mirror.cuh"
+#include "kernels_sort.cuh"
+#include "kernels_transform.cuh"
+
+using namespace astre;
+
+static_assert(sizeof(astre_host::ViewHost) == sizeof(ViewDev), "host/device view records must match");
+static_assert(sizeof(astre_mesh_bounds) == sizeof(BoundsDev), "bounds records must match");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Level {
+    uint32_t first = 0, count = 0;  // range [first, first+count) when contiguous
+    bool contiguous = true;
+    size_t list_offset = 0;         // offset into d_level_slots otherwise
+};
+
+}  // namespace
+
+struct astre_gpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    uint32_t max_entities = 0, cap_entities = 0, max_views = 0;
+    uint64_t max_keys = 0;
+    uint32_t n_entities = 0;
+    cudaStream_t stream = nullptr;
+
+    // mirror
+    float *d_planes = nullptr;       // 10 planes of cap_entities floats
+    float *d_prev = nullptr;         // previous-tick TRS planes (lazy; interpolation)
+    uint32_t *d_meta = nullptr, *d_parent = nullptr;
+    float4 *d_world = nullptr;
+    float *d_basis = nullptr;        // fwd3 | up3 | right3, packed (lazy)
+    BoundsDev *d_bounds = nullptr;
+    uint32_t n_meshes = 0, cap_meshes = 0;
+    ViewDev *d_views = nullptr;
+    uint32_t cap_view_records = 0;
+    uint32_t n_worlds = 1, entities_per_world = 0, views_per_world = 0, world_bits = 0;
+
+    // frame outputs
+    unsigned long long *d_keys[2] = {nullptr, nullptr};
+    uint32_t *d_counts = nullptr;
+    unsigned long long *d_offsets = nullptr;
+    uint32_t cap_counts = 0;
+    FrameControl *d_ctl = nullptr;
+    SortControl *d_sc = nullptr;
+    unsigned long long *d_lookback = nullptr;
+    float4 *d_gather = nullptr;
+    uint64_t cap_gather = 0;
+    uint32_t epoch = 0;
+
+    // staging for uploads
+    unsigned char *d_stage = nullptr;
+    uint32_t stage_entities = 0;
+
+    // hierarchy
+    std::vector<uint32_t> h_parent;
+    bool has_parents = false, hier_dirty = false;
+    std::vector<Level> levels;
+    uint32_t *d_level_slots = nullptr;
+    size_t cap_level_slots = 0;
+
+    std::vector<uint64_t> h_entity_id;
+
+    // cached read-backs of the last frame
+    bool frame_done = false, results_cached = false;
+    uint32_t last_flags = 0;
+    std::vector<uint32_t> h_counts;
+    std::vector<unsigned long long> h_offsets;
+    unsigned long long h_total = 0;
+    uint32_t h_overflow = 0, h_result_buf = 0;
+
+    cudaEvent_t ev_begin = nullptr, ev_cull0 = nullptr, ev_cull1 = nullptr, ev_end = nullptr;
+    cudaStream_t last_stream = nullptr;
+    uint64_t launches = 0;
+    int cull_blocks_per_sm = 2;
+    std::string err;
+
+    float *plane(int i) const { return d_planes + (size_t)i * cap_entities; }
+    float *prev(int i) const { return d_prev + (size_t)i * cap_entities; }
+};
+
+namespace {
+
+int fail(astre_gpu_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, ASTRE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+#define CK_LAUNCH()                                                                                \
+    do {                                                                                           \
+        ++ctx->launches;                                                                           \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, ASTRE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+inline uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+Planes planes_of(const astre_gpu_ctx *c)
+{
+    Planes p;
+    p.px = c->plane(0); p.py = c->plane(1); p.pz = c->plane(2);
+    p.qx = c->plane(3); p.qy = c->plane(4); p.qz = c->plane(5); p.qw = c->plane(6);
+    p.sx = c->plane(7); p.sy = c->plane(8); p.sz = c->plane(9);
+    return p;
+}
+
+FrameParams params_of(const astre_gpu_ctx *c, bool cull)
+{
+    FrameParams P;
+    P.px = c->plane(0); P.py = c->plane(1); P.pz = c->plane(2);
+    P.qx = c->plane(3); P.qy = c->plane(4); P.qz = c->plane(5); P.qw = c->plane(6);
+    P.sx = c->plane(7); P.sy = c->plane(8); P.sz = c->plane(9);
+    P.meta = c->d_meta;
+    P.parent = c->d_parent;
+    P.world = c->d_world;
+    P.bounds = c->d_bounds;
+    P.views = c->d_views;
+    P.keys = c->d_keys[0];
+    P.counts = c->d_counts;
+    P.ctl = c->d_ctl;
+    P.key_cap = c->max_keys;
+    P.n_meshes = c->n_meshes;
+    P.views_per_world = cull ? c->views_per_world : 0u;
+    P.n_worlds = c->n_worlds;
+    P.entities_per_world = c->n_worlds > 1 ? c->entities_per_world : 0u;
+    P.world_bits = c->world_bits;
+    return P;
+}
+
+__global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts, uint32_t epoch)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        ctl->key_total = 0; ctl->overflow = 0; ctl->pad = 0;
+        sc->result_buf = 0; sc->n_keys = 0; sc->epoch = epoch;
+    }
+    for (uint32_t i = tid; i < kSortPasses * 256; i += nth) (&sc->hist[0][0])[i] = 0;
+    for (uint32_t i = tid; i < kSortPasses; i += nth) { sc->skip[i] = 1; sc->src[i] = 0; sc->tile_counter[i] = 0; }
+    for (uint32_t i = tid; i < n_counts; i += nth) counts[i] = 0;
+}
+
+// Depth of every slot; returns the level count or -1 (bad index / cycle).
+int compute_depths(const std::vector<uint32_t> &parent, uint32_t n, std::vector<uint32_t> &depth)
+{
+    const uint32_t UNSET = 0xFFFFFFFFu;
+    depth.assign(n, UNSET);
+    int levels = 0;
+    std::vector<uint32_t> chain;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (depth[i] != UNSET) continue;
+        chain.clear();
+        uint32_t cur = i;
+        while (depth[cur] == UNSET) {
+            chain.push_back(cur);
+            const uint32_t p = parent[cur];
+            if (p == ASTRE_NO_PARENT) break;
+            if (p >= n || chain.size() > n) return -1;
+            cur = p;
+        }
+        uint32_t d;
+        if (depth[cur] != UNSET) d = depth[cur] + 1;       // stopped at a known ancestor
+        else { d = 0; }                                      // stopped at a root (last pushed)
+        // chain is child ... ancestor-most; assign from the top down
+        for (size_t k = chain.size(); k-- > 0;) {
+            const uint32_t s = chain[k];
+            if (depth[s] != UNSET) continue;
+            depth[s] = d++;
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) levels = std::max(levels, (int)depth[i] + 1);
+    return levels;
+}
+
+int rebuild_levels(astre_gpu_ctx *ctx)
+{
+    const uint32_t n = ctx->n_entities;
+    ctx->levels.clear();
+    ctx->has_parents = false;
+    for (uint32_t i = 0; i < n; ++i)
+        if (ctx->h_parent[i] != ASTRE_NO_PARENT) { ctx->has_parents = true; break; }
+    ctx->hier_dirty = false;
+    if (!ctx->has_parents) return ASTRE_OK;
+
+    std::vector<uint32_t> depth;
+    const int n_levels = compute_depths(ctx->h_parent, n, depth);
+    if (n_levels < 0) {
+        ctx->hier_dirty = true;
+        return fail(ctx, ASTRE_ERR_HIERARCHY, "parent index out of range or cyclic parent links");
+    }
+    // counting sort of slots by depth (stable: slots ascend inside a level)
+    std::vector<size_t> start(n_levels + 1, 0);
+    for (uint32_t i = 0; i < n; ++i) ++start[depth[i] + 1];
+    for (int l = 0; l < n_levels; ++l) start[l + 1] += start[l];
+    std::vector<uint32_t> order(n);
+    {
+        std::vector<size_t> fill(start.begin(), start.end() - 1);
+        for (uint32_t i = 0; i < n; ++i) order[fill[depth[i]]++] = i;
+    }
+    ctx->levels.resize(n_levels);
+    bool any_list = false;
+    for (int l = 0; l < n_levels; ++l) {
+        Level &L = ctx->levels[l];
+        L.count = (uint32_t)(start[l + 1] - start[l]);
+        L.first = order[start[l]];
+        L.contiguous = (order[start[l + 1] - 1] - L.first + 1 == L.count);
+        L.list_offset = start[l];
+        any_list |= !L.contiguous;
+    }
+    if (any_list) {
+        if (ctx->cap_level_slots < n) {
+            if (ctx->d_level_slots) cudaFree(ctx->d_level_slots);
+            ctx->d_level_slots = nullptr;
+            CK(cudaMalloc(&ctx->d_level_slots, (size_t)ctx->cap_entities * sizeof(uint32_t)));
+            ctx->cap_level_slots = ctx->cap_entities;
+        }
+        CK(cudaMemcpyAsync(ctx->d_level_slots, order.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return ASTRE_OK;
+}
+
+int cache_results(astre_gpu_ctx *ctx)
+{
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    if (ctx->results_cached) return ASTRE_OK;
+    cudaStream_t s = ctx->last_stream;
+    const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
+    FrameControl ctl;
+    SortControl *sc_host = nullptr;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpy(&ctl, ctx->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
+    uint32_t result_buf = 0;
+    CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    (void)sc_host;
+    ctx->h_counts.assign(n_counts, 0);
+    ctx->h_offsets.assign((size_t)n_counts + 1, 0);
+    if (n_counts) {
+        CK(cudaMemcpy(ctx->h_counts.data(), ctx->d_counts, (size_t)n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ctx->h_offsets.data(), ctx->d_offsets, ((size_t)n_counts + 1) * sizeof(unsigned long long),
+                      cudaMemcpyDeviceToHost));
+    }
+    ctx->h_total = ctl.key_total;
+    ctx->h_overflow = (ctl.key_total > ctx->max_keys) ? 1u : ctl.overflow;
+    ctx->h_result_buf = result_buf;
+    ctx->results_cached = true;
+    return ASTRE_OK;
+}
+
+int ensure_stage(astre_gpu_ctx *ctx)
+{
+    if (ctx->d_stage) return ASTRE_OK;
+    ctx->stage_entities = std::min<uint32_t>(std::max<uint32_t>(ctx->max_entities, 1u), 1u << 20);
+    CK(cudaMalloc(&ctx->d_stage, (size_t)ctx->stage_entities * 64));
+    return ASTRE_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+const char *astre_gpu_version(void) { return "astre-b200 0.1 (sm_100a)"; }
+
+const char *astre_gpu_last_error(const astre_gpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_views, uint64_t max_keys)
+{
+    astre_gpu_ctx *none = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        fail(none, ASTRE_ERR_CUDA, "no CUDA device available (%s); libastre_gpu has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return nullptr;
+    }
+    if (device < 0 || device >= n_dev) { fail(none, ASTRE_ERR_INVALID, "device %d out of range (0..%d)", device, n_dev - 1); return nullptr; }
+    if (max_entities == 0 || max_entities > (1u << ASTRE_KEY_SLOT_BITS)) {
+        fail(none, ASTRE_ERR_INVALID, "max_entities must be in 1..2^26 (slot field of the draw key)");
+        return nullptr;
+    }
+    if (max_views > ASTRE_MAX_VIEWS) { fail(none, ASTRE_ERR_INVALID, "max_views must be <= %d", ASTRE_MAX_VIEWS); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        fail(none, ASTRE_ERR_CUDA, "cannot select device %d", device);
+        return nullptr;
+    }
+    if (prop.major < 10) {
+        fail(none, ASTRE_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    astre_gpu_ctx *ctx = new (std::nothrow) astre_gpu_ctx();
+    if (!ctx) { fail(none, ASTRE_ERR_INVALID, "out of host memory"); return nullptr; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_entities = max_entities;
+    ctx->cap_entities = (uint32_t)((((uint64_t)max_entities + kBlockTile - 1) / kBlockTile) * kBlockTile + kBlockTile);
+    ctx->max_views = max_views;
+    ctx->max_keys = max_keys ? max_keys : (uint64_t)max_entities * std::max<uint32_t>(max_views, 1u);
+    if (ctx->max_keys > 0xFFFFFFF0ull) ctx->max_keys = 0xFFFFFFF0ull;
+
+    auto bail = [&](const char *what, cudaError_t err) -> astre_gpu_ctx * {
+        fail(none, ASTRE_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(err));
+        astre_gpu_destroy(ctx);
+        return nullptr;
+    };
+#define CKC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) return bail(#call, e2_); } while (0)
+    const size_t cap = ctx->cap_entities;
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&ctx->d_planes, cap * 10 * sizeof(float)));
+    CKC(cudaMemset(ctx->d_planes, 0, cap * 10 * sizeof(float)));
+    CKC(cudaMalloc(&ctx->d_meta, cap * sizeof(uint32_t)));
+    CKC(cudaMemset(ctx->d_meta, 0, cap * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_parent, cap * sizeof(uint32_t)));
+    CKC(cudaMemset(ctx->d_parent, 0xFF, cap * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_world, cap * 4 * sizeof(float4)));
+    ctx->cap_meshes = 16;
+    CKC(cudaMalloc(&ctx->d_bounds, ctx->cap_meshes * sizeof(BoundsDev)));
+    CKC(cudaMemset(ctx->d_bounds, 0, ctx->cap_meshes * sizeof(BoundsDev)));
+    ctx->cap_view_records = std::max<uint32_t>(max_views, 1u);
+    CKC(cudaMalloc(&ctx->d_views, ctx->cap_view_records * sizeof(ViewDev)));
+    CKC(cudaMemset(ctx->d_views, 0, ctx->cap_view_records * sizeof(ViewDev)));
+    CKC(cudaMalloc(&ctx->d_keys[0], ctx->max_keys * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&ctx->d_keys[1], ctx->max_keys * sizeof(unsigned long long)));
+    ctx->cap_counts = std::max<uint32_t>(max_views, 1u);
+    CKC(cudaMalloc(&ctx->d_counts, ctx->cap_counts * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_offsets, ((size_t)ctx->cap_counts + 1) * sizeof(unsigned long long)));
+    CKC(cudaMalloc(&ctx->d_ctl, sizeof(FrameControl)));
+    CKC(cudaMemset(ctx->d_ctl, 0, sizeof(FrameControl)));
+    CKC(cudaMalloc(&ctx->d_sc, sizeof(SortControl)));
+    CKC(cudaMemset(ctx->d_sc, 0, sizeof(SortControl)));
+    const size_t n_sort_tiles = (size_t)((ctx->max_keys + kSortTile - 1) / kSortTile) + 1;
+    CKC(cudaMalloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
+    CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
+    CKC(cudaEventCreate(&ctx->ev_begin));
+    CKC(cudaEventCreate(&ctx->ev_cull0));
+    CKC(cudaEventCreate(&ctx->ev_cull1));
+    CKC(cudaEventCreate(&ctx->ev_end));
+    const int stage_bytes = kWarpsPerBlock * kStageF4PerWarp * (int)sizeof(float4);
+    CKC(cudaFuncSetAttribute(k_transform_cull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+    CKC(cudaFuncSetAttribute(k_transform_cull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+    int occ = 0;
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_transform_cull<false>, kBlockThreads, stage_bytes));
+    ctx->cull_blocks_per_sm = std::max(occ, 1);
+    CKC(cudaDeviceSynchronize());
+#undef CKC
+    ctx->h_parent.assign(max_entities, ASTRE_NO_PARENT);
+    return ctx;
+}
+
+void astre_gpu_destroy(astre_gpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = { ctx->d_planes, ctx->d_prev, ctx->d_meta, ctx->d_parent, ctx->d_world, ctx->d_basis, ctx->d_bounds,
+                     ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots };
+    for (void *p : ptrs) if (p) cudaFree(p);
+    cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int astre_gpu_set_entity_count(astre_gpu_ctx *ctx, uint32_t n)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (n > ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "entity count %u exceeds max_entities %u", n, ctx->max_entities);
+    if (n != ctx->n_entities) ctx->hier_dirty = true;
+    ctx->n_entities = n;
+    return ASTRE_OK;
+}
+
+int astre_gpu_upload_entities(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, const uint64_t *entity_id,
+                              const float *pos3, const float *rot4, const float *scl3, const uint32_t *parent_slot,
+                              const uint32_t *mesh_id, const uint32_t *shader_id, const uint8_t *flags)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if ((uint64_t)first + count > ctx->max_entities)
+        return fail(ctx, ASTRE_ERR_INVALID, "slots [%u, %u) exceed max_entities %u", first, first + count, ctx->max_entities);
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_stage(ctx)) return rc;
+    cudaStream_t s = ctx->stream;
+    const Planes pl = planes_of(ctx);
+    for (uint32_t done = 0; done < count;) {
+        const uint32_t c = std::min(ctx->stage_entities, count - done);
+        unsigned char *st = ctx->d_stage;
+        float *d_pos = (float *)st;                       st += (size_t)c * 12;
+        float *d_scl = (float *)st;                       st += (size_t)c * 12;
+        st = ctx->d_stage + (((size_t)(st - ctx->d_stage) + 15) & ~(size_t)15);
+        float *d_rot = (float *)st;                       st += (size_t)c * 16;
+        uint32_t *d_mesh = (uint32_t *)st;                st += (size_t)c * 4;
+        uint32_t *d_shader = (uint32_t *)st;              st += (size_t)c * 4;
+        uint32_t *d_par = (uint32_t *)st;                 st += (size_t)c * 4;
+        uint8_t *d_flags = (uint8_t *)st;
+        if (pos3) CK(cudaMemcpyAsync(d_pos, pos3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
+        if (rot4) CK(cudaMemcpyAsync(d_rot, rot4 + 4 * (size_t)done, (size_t)c * 16, cudaMemcpyHostToDevice, s));
+        if (scl3) CK(cudaMemcpyAsync(d_scl, scl3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
+        if (mesh_id) CK(cudaMemcpyAsync(d_mesh, mesh_id + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
+        if (shader_id) CK(cudaMemcpyAsync(d_shader, shader_id + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
+        if (parent_slot) CK(cudaMemcpyAsync(d_par, parent_slot + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
+        if (flags) CK(cudaMemcpyAsync(d_flags, flags + done, (size_t)c, cudaMemcpyHostToDevice, s));
+        const uint32_t grid = std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8);
+        k_ingest_trs<<<grid, 256, 0, s>>>(pl, nullptr, first + done, c, pos3 ? d_pos : nullptr, rot4 ? d_rot : nullptr,
+                                          scl3 ? d_scl : nullptr, true);
+        CK_LAUNCH();
+        k_ingest_meta<<<grid, 256, 0, s>>>(ctx->d_meta, ctx->d_parent, first + done, c, mesh_id ? d_mesh : nullptr,
+                                           shader_id ? d_shader : nullptr, flags ? d_flags : nullptr,
+                                           parent_slot ? d_par : nullptr);
+        CK_LAUNCH();
+        done += c;
+    }
+    CK(cudaStreamSynchronize(s));   // host buffers may be reused by the caller
+    for (uint32_t i = 0; i < count; ++i) ctx->h_parent[first + i] = parent_slot ? parent_slot[i] : ASTRE_NO_PARENT;
+    if (entity_id) {
+        if (ctx->h_entity_id.empty()) {
+            ctx->h_entity_id.resize(ctx->max_entities);
+            for (uint32_t i = 0; i < ctx->max_entities; ++i) ctx->h_entity_id[i] = i;
+        }
+        std::memcpy(ctx->h_entity_id.data() + first, entity_id, (size_t)count * sizeof(uint64_t));
+    }
+    ctx->hier_dirty = true;
+    ctx->n_entities = std::max(ctx->n_entities, first + count);
+    return ASTRE_OK;
+}
+
+static int update_trs_impl(astre_gpu_ctx *ctx, const uint32_t *slots, uint32_t first, uint32_t n,
+                           const float *pos3, const float *rot4, const float *scl3)
+{
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_stage(ctx)) return rc;
+    cudaStream_t s = ctx->stream;
+    const Planes pl = planes_of(ctx);
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t c = std::min(ctx->stage_entities, n - done);
+        unsigned char *st = ctx->d_stage;
+        float *d_pos = (float *)st;                       st += (size_t)c * 12;
+        float *d_scl = (float *)st;                       st += (size_t)c * 12;
+        st = ctx->d_stage + (((size_t)(st - ctx->d_stage) + 15) & ~(size_t)15);
+        float *d_rot = (float *)st;                       st += (size_t)c * 16;
+        uint32_t *d_slots = (uint32_t *)st;
+        if (slots) CK(cudaMemcpyAsync(d_slots, slots + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
+        if (pos3) CK(cudaMemcpyAsync(d_pos, pos3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
+        if (rot4) CK(cudaMemcpyAsync(d_rot, rot4 + 4 * (size_t)done, (size_t)c * 16, cudaMemcpyHostToDevice, s));
+        if (scl3) CK(cudaMemcpyAsync(d_scl, scl3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
+        const uint32_t grid = std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8);
+        k_ingest_trs<<<grid, 256, 0, s>>>(pl, slots ? d_slots : nullptr, first + done, c, pos3 ? d_pos : nullptr,
+                                          rot4 ? d_rot : nullptr, scl3 ? d_scl : nullptr, false);
+        CK_LAUNCH();
+        done += c;
+    }
+    CK(cudaStreamSynchronize(s));
+    return ASTRE_OK;
+}
+
+int astre_gpu_update_trs(astre_gpu_ctx *ctx, uint32_t n, const uint32_t *slots, const float *pos3, const float *rot4,
+                         const float *scl3)
+{
+    if (!ctx || (n && !slots)) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "slots is null") : ASTRE_ERR_INVALID;
+    for (uint32_t i = 0; i < n; ++i)
+        if (slots[i] >= ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot %u out of range", slots[i]);
+    return update_trs_impl(ctx, slots, 0, n, pos3, rot4, scl3);
+}
+
+int astre_gpu_update_trs_range(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, const float *pos3, const float *rot4,
+                               const float *scl3)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if ((uint64_t)first + count > ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot range out of bounds");
+    return update_trs_impl(ctx, nullptr, first, count, pos3, rot4, scl3);
+}
+
+int astre_gpu_update_flags(astre_gpu_ctx *ctx, uint32_t n, const uint32_t *slots, const uint8_t *flags)
+{
+    if (!ctx || (n && (!slots || !flags))) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "null argument") : ASTRE_ERR_INVALID;
+    for (uint32_t i = 0; i < n; ++i)
+        if (slots[i] >= ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot %u out of range", slots[i]);
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_stage(ctx)) return rc;
+    cudaStream_t s = ctx->stream;
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t c = std::min(ctx->stage_entities, n - done);
+        uint32_t *d_slots = (uint32_t *)ctx->d_stage;
+        uint8_t *d_flags = ctx->d_stage + (size_t)c * 4;
+        CK(cudaMemcpyAsync(d_slots, slots + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_flags, flags + done, (size_t)c, cudaMemcpyHostToDevice, s));
+        k_update_flags<<<std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8), 256, 0, s>>>(ctx->d_meta, d_slots, d_flags, c);
+        CK_LAUNCH();
+        done += c;
+    }
+    CK(cudaStreamSynchronize(s));
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_mesh_bounds(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre_mesh_bounds *bounds)
+{
+    if (!ctx || (n_meshes && !bounds)) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "bounds is null") : ASTRE_ERR_INVALID;
+    if (n_meshes > (1u << ASTRE_KEY_MESH_BITS)) return fail(ctx, ASTRE_ERR_INVALID, "at most 2048 meshes (mesh field of the draw key)");
+    CK(cudaSetDevice(ctx->device));
+    if (n_meshes > ctx->cap_meshes) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(ctx->d_bounds));
+        ctx->d_bounds = nullptr;
+        CK(cudaMalloc(&ctx->d_bounds, (size_t)n_meshes * sizeof(BoundsDev)));
+        ctx->cap_meshes = n_meshes;
+    }
+    if (n_meshes) {
+        CK(cudaMemcpyAsync(ctx->d_bounds, bounds, (size_t)n_meshes * sizeof(BoundsDev), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->n_meshes = n_meshes;
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t entities_per_world, uint32_t views_per_world,
+                              const float *clip16, const uint8_t *phase_mask)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (n_worlds == 0) return fail(ctx, ASTRE_ERR_INVALID, "n_worlds must be >= 1");
+    if (views_per_world > ctx->max_views) return fail(ctx, ASTRE_ERR_INVALID, "%u views exceed max_views %u", views_per_world, ctx->max_views);
+    if (views_per_world && (!clip16 || !phase_mask)) return fail(ctx, ASTRE_ERR_INVALID, "null view arrays");
+    uint32_t wbits = 0;
+    while ((1u << wbits) < n_worlds) ++wbits;
+    if (n_worlds > 1) {
+        if (entities_per_world == 0 || entities_per_world % 4)
+            return fail(ctx, ASTRE_ERR_INVALID, "entities_per_world must be a positive multiple of 4");
+        if ((uint64_t)n_worlds * entities_per_world > ctx->max_entities)
+            return fail(ctx, ASTRE_ERR_INVALID, "n_worlds * entities_per_world exceeds max_entities");
+        if (wbits > 20 || entities_per_world > (1u << (ASTRE_KEY_SLOT_BITS - wbits)))
+            return fail(ctx, ASTRE_ERR_INVALID, "world index and local slot do not fit the 26-bit key field");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n_rec = (uint64_t)n_worlds * views_per_world;
+    if (n_rec > 0xFFFFFFFFull) return fail(ctx, ASTRE_ERR_INVALID, "too many view records");
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_rec > ctx->cap_view_records) {
+        CK(cudaFree(ctx->d_views)); ctx->d_views = nullptr;
+        CK(cudaMalloc(&ctx->d_views, n_rec * sizeof(ViewDev)));
+        ctx->cap_view_records = (uint32_t)n_rec;
+    }
+    if (n_rec > ctx->cap_counts) {
+        CK(cudaFree(ctx->d_counts)); ctx->d_counts = nullptr;
+        CK(cudaFree(ctx->d_offsets)); ctx->d_offsets = nullptr;
+        CK(cudaMalloc(&ctx->d_counts, n_rec * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_offsets, (n_rec + 1) * sizeof(unsigned long long)));
+        ctx->cap_counts = (uint32_t)n_rec;
+    }
+    std::vector<astre_host::ViewHost> recs(n_rec);
+    for (uint64_t i = 0; i < n_rec; ++i)
+        astre_host::extract_view(clip16 + 16 * i, phase_mask[i % views_per_world] & 15u, &recs[i]);
+    if (n_rec) CK(cudaMemcpy(ctx->d_views, recs.data(), n_rec * sizeof(ViewDev), cudaMemcpyHostToDevice));
+    ctx->n_worlds = n_worlds;
+    ctx->entities_per_world = n_worlds > 1 ? entities_per_world : 0;
+    ctx->views_per_world = views_per_world;
+    ctx->world_bits = wbits;
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_views(astre_gpu_ctx *ctx, uint32_t n_views, const float *clip16, const uint8_t *phase_mask)
+{
+    return astre_gpu_set_world_views(ctx, 1, 0, n_views, clip16, phase_mask);
+}
+
+int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->hier_dirty) if (int rc = rebuild_levels(ctx)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n = ctx->n_entities;
+    const bool cull = (stage_flags & ASTRE_FRAME_CULL) && ctx->views_per_world > 0;
+    const bool sort = cull && (stage_flags & ASTRE_FRAME_SORT);
+    const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
+    if (ctx->n_worlds > 1 && (uint64_t)ctx->n_worlds * ctx->entities_per_world < n)
+        return fail(ctx, ASTRE_ERR_STATE, "entity count %u exceeds n_worlds*entities_per_world", n);
+
+    ctx->epoch = (ctx->epoch + 1) & ((1u << 27) - 1u);
+    if (ctx->epoch == 0) {   // tag wrapped: clear stale look-back words once
+        const size_t n_sort_tiles = (size_t)((ctx->max_keys + kSortTile - 1) / kSortTile) + 1;
+        CK(cudaMemsetAsync(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long), s));
+        ctx->epoch = 1;
+    }
+    CK(cudaEventRecord(ctx->ev_begin, s));
+    k_frame_begin<<<8, 256, 0, s>>>(ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch);
+    CK_LAUNCH();
+
+    const FrameParams P = params_of(ctx, cull);
+    const int stage_bytes = kWarpsPerBlock * kStageF4PerWarp * (int)sizeof(float4);
+    const uint32_t max_grid = (uint32_t)(ctx->sm_count * ctx->cull_blocks_per_sm);
+    CK(cudaEventRecord(ctx->ev_cull0, s));
+    if (n) {
+        if (!ctx->has_parents) {
+            const uint32_t tiles = ceil_div(n, kBlockTile);
+            k_transform_cull<false><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, 0u, n);
+            CK_LAUNCH();
+        } else {
+            for (size_t l = 0; l < ctx->levels.size(); ++l) {
+                const Level &L = ctx->levels[l];
+                if (L.contiguous) {
+                    const uint32_t base0 = L.first & ~(uint32_t)(kWarpTile - 1);
+                    const uint32_t tiles = ceil_div((uint64_t)L.first + L.count - base0, kBlockTile);
+                    if (l == 0)
+                        k_transform_cull<false><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, L.first, L.first + L.count);
+                    else
+                        k_transform_cull<true><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, L.first, L.first + L.count);
+                } else {
+                    const uint32_t grid = std::min<uint32_t>(ceil_div(L.count, kBlockThreads), (uint32_t)ctx->sm_count * 8);
+                    k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(P, ctx->d_level_slots + L.list_offset, L.count);
+                }
+                CK_LAUNCH();
+            }
+        }
+    }
+    CK(cudaEventRecord(ctx->ev_cull1, s));
+
+    if (stage_flags & ASTRE_FRAME_BASIS) {
+        if (!ctx->d_basis) CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
+        if (n) {
+            float *b = ctx->d_basis;
+            const size_t stride = (size_t)ctx->cap_entities * 3;
+            k_basis<<<std::min<uint32_t>(ceil_div(n, 256), ctx->sm_count * 8), 256, 0, s>>>(
+                ctx->plane(3), ctx->plane(4), ctx->plane(5), ctx->plane(6), b, b + stride, b + 2 * stride, n);
+            CK_LAUNCH();
+        }
+    }
+
+    if (sort) {
+        const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
+        k_sort_hist<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_ctl, ctx->max_keys, ctx->d_sc);
+        CK_LAUNCH();
+        k_sort_plan<<<1, kSortPasses * 32, 0, s>>>(ctx->d_ctl, ctx->max_keys, ctx->d_sc);
+        CK_LAUNCH();
+        for (int p = 0; p < kSortPasses; ++p) {
+            k_sort_pass<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, p);
+            CK_LAUNCH();
+        }
+    }
+    if (n_counts) {
+        k_scan_counts<<<1, 1024, 0, s>>>(ctx->d_counts, ctx->d_offsets, n_counts);
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ctx->ev_end, s));
+    ctx->frame_done = true;
+    ctx->results_cached = false;
+    ctx->last_flags = stage_flags;
+    ctx->last_stream = s;
+    return ASTRE_OK;
+}
+
+int astre_gpu_sync(astre_gpu_ctx *ctx)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));
+    return ASTRE_OK;
+}
+
+uint64_t astre_gpu_launch_count(const astre_gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int astre_gpu_last_frame_ms(astre_gpu_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    CK(cudaEventSynchronize(ctx->ev_end));
+    CK(cudaEventElapsedTime(ms, ctx->ev_begin, ctx->ev_end));
+    return ASTRE_OK;
+}
+
+int astre_gpu_last_cull_ms(astre_gpu_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    CK(cudaEventSynchronize(ctx->ev_cull1));
+    CK(cudaEventElapsedTime(ms, ctx->ev_cull0, ctx->ev_cull1));
+    return ASTRE_OK;
+}
+
+int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (!ctx->d_prev) CK(cudaMalloc(&ctx->d_prev, (size_t)ctx->cap_entities * 10 * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->d_prev, ctx->d_planes, (size_t)ctx->cap_entities * 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return ASTRE_OK;
+}
+
+int astre_gpu_interpolate(astre_gpu_ctx *ctx, float alpha, void *stream)
+{
+    (void)alpha; (void)stream;
+    if (!ctx) return ASTRE_ERR_INVALID;
+    return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_interpolate is not built yet");
+}
+
+int astre_gpu_read_world(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, float *out)
+{
+    if (!ctx || (count && !out)) return ASTRE_ERR_INVALID;
+    if ((uint64_t)first + count > ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    if (count) CK(cudaMemcpy(out, ctx->d_world + (size_t)first * 4, (size_t)count * 64, cudaMemcpyDeviceToHost));
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_basis(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, float *fwd3, float *up3, float *right3)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (!ctx->d_basis) return fail(ctx, ASTRE_ERR_STATE, "no frame with ASTRE_FRAME_BASIS has been run");
+    if ((uint64_t)first + count > ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    const size_t stride = (size_t)ctx->cap_entities * 3;
+    float *outs[3] = { fwd3, up3, right3 };
+    for (int i = 0; i < 3; ++i)
+        if (outs[i] && count)
+            CK(cudaMemcpy(outs[i], ctx->d_basis + i * stride + (size_t)first * 3, (size_t)count * 12, cudaMemcpyDeviceToHost));
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_counts(astre_gpu_ctx *ctx, uint32_t *counts)
+{
+    if (!ctx || !counts) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    std::memcpy(counts, ctx->h_counts.data(), ctx->h_counts.size() * sizeof(uint32_t));
+    if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_total(astre_gpu_ctx *ctx, uint64_t *total)
+{
+    if (!ctx || !total) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    *total = ctx->h_total;
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_all_keys(astre_gpu_ctx *ctx, uint64_t *keys, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    const uint64_t have = std::min<uint64_t>(ctx->h_total, ctx->max_keys);
+    *n_out = have;
+    const uint64_t c = std::min(have, cap);
+    if (c && keys) CK(cudaMemcpy(keys, ctx->d_keys[ctx->h_result_buf], c * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_keys(astre_gpu_ctx *ctx, uint32_t world, uint32_t view, uint64_t *keys, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    if (world >= ctx->n_worlds || view >= ctx->views_per_world) return fail(ctx, ASTRE_ERR_INVALID, "world/view out of range");
+    if (!(ctx->last_flags & ASTRE_FRAME_SORT)) return fail(ctx, ASTRE_ERR_STATE, "per-view lists need ASTRE_FRAME_SORT");
+    if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
+    const size_t u = (size_t)world * ctx->views_per_world + view;
+    const uint64_t off = ctx->h_offsets[u], cnt = ctx->h_counts[u];
+    *n_out = cnt;
+    const uint64_t c = std::min(cnt, cap);
+    if (c && keys) CK(cudaMemcpy(keys, ctx->d_keys[ctx->h_result_buf] + off, c * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_t n, float *out)
+{
+    if (!ctx || (n && !out)) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    const uint64_t have = std::min<uint64_t>(ctx->h_total, ctx->max_keys);
+    if (first_key + n > have) return fail(ctx, ASTRE_ERR_INVALID, "key range [%llu, %llu) exceeds the %llu keys of the frame",
+                                          (unsigned long long)first_key, (unsigned long long)(first_key + n), (unsigned long long)have);
+    if (!n) return ASTRE_OK;
+    if (ctx->cap_gather < n) {
+        if (ctx->d_gather) CK(cudaFree(ctx->d_gather));
+        ctx->d_gather = nullptr;
+        CK(cudaMalloc(&ctx->d_gather, n * 64));
+        ctx->cap_gather = n;
+    }
+    cudaStream_t s = ctx->last_stream;
+    const uint32_t grid = std::min<uint32_t>(ceil_div(n * 4, 256), (uint32_t)ctx->sm_count * 8);
+    k_gather_world<<<grid, 256, 0, s>>>(ctx->d_keys[ctx->h_result_buf], first_key, n, ctx->d_world, ctx->d_gather,
+                                        ctx->world_bits, ctx->entities_per_world);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(out, ctx->d_gather, n * 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ASTRE_OK;
+}
+
+int astre_gpu_slot_entity(const astre_gpu_ctx *ctx, uint32_t slot, uint64_t *entity_id)
+{
+    if (!ctx || !entity_id || slot >= ctx->max_entities) return ASTRE_ERR_INVALID;
+    *entity_id = ctx->h_entity_id.empty() ? slot : ctx->h_entity_id[slot];
+    return ASTRE_OK;
+}
+
+void *astre_gpu_device_world(astre_gpu_ctx *ctx) { return ctx ? ctx->d_world : nullptr; }
+void *astre_gpu_device_counts(astre_gpu_ctx *ctx) { return ctx ? ctx->d_counts : nullptr; }
+void *astre_gpu_device_sorted_keys(astre_gpu_ctx *ctx)
+{
+    if (!ctx || cache_results(ctx) != ASTRE_OK) return nullptr;
+    return ctx->d_keys[ctx->h_result_buf];
+}
+
+// ---- host-side helpers -------------------------------------------------------
+
+void astre_camera_matrices(const float *pos3, const float *fwd3, const float *up3, float fov_deg, float aspect,
+                           float z_near, float z_far, float *view16, float *proj16, float *clip16)
+{
+    using namespace astre_host;
+    float view[16], proj[16];
+    const V3 eye = { pos3[0], pos3[1], pos3[2] };
+    const V3 center = { pos3[0] + fwd3[0], pos3[1] + fwd3[1], pos3[2] + fwd3[2] };
+    look_at(eye, center, V3{ up3[0], up3[1], up3[2] }, view);
+    perspective(radians(fov_deg), aspect, z_near, z_far, proj);
+    if (view16) std::memcpy(view16, view, sizeof view);
+    if (proj16) std::memcpy(proj16, proj, sizeof proj);
+    if (clip16) mat_mul(proj, view, clip16);
+}
+
+int astre_light_space_matrix(const float *pos3, const float *dir3, int type, float outer_cutoff, float *clip16)
+{
+    using namespace astre_host;
+    float view[16], proj[16];
+    const V3 eye = { pos3[0], pos3[1], pos3[2] };
+    const V3 d = normalize(V3{ dir3[0], dir3[1], dir3[2] });
+    look_at(eye, V3{ eye.x + d.x, eye.y + d.y, eye.z + d.z }, V3{ 0.0f, 1.0f, 0.0f }, view);
+    if (type == 1) {
+        ortho(-100.0f, 100.0f, -100.0f, 100.0f, 0.1f, 100.0f, proj);
+    } else if (type == 3) {
+        const float outer = clampf(outer_cutoff, -1.0f, 1.0f);
+        float fov = degrees(2.0f * std::acos(clampf(outer, -0.999f, 0.999f)));
+        fov = clampf(fov, 5.0f, 179.0f);
+        perspective(radians(fov), 1.7f, 0.1f, 1024.0f, proj);
+    } else if (type == 2) {
+        perspective(radians(90.0f), 1.0f, 0.1f, 100.0f, proj);
+    } else {
+        return 0;
+    }
+    mat_mul(proj, view, clip16);
+    return 1;
+}
+
+void astre_ortho_view_matrix(const float *eye3, const float *center3, const float *up3, float l, float r, float b,
+                             float t, float n, float f, float *clip16)
+{
+    using namespace astre_host;
+    float view[16], proj[16];
+    look_at(V3{ eye3[0], eye3[1], eye3[2] }, V3{ center3[0], center3[1], center3[2] }, V3{ up3[0], up3[1], up3[2] }, view);
+    ortho(l, r, b, t, n, f, proj);
+    mat_mul(proj, view, clip16);
+}
+
+void astre_global_offsets(const uint32_t *all_counts, uint32_t world_size, uint32_t rank, uint32_t n_views,
+                          uint64_t *offsets, uint64_t *view_totals)
+{
+    uint64_t run = 0;
+    for (uint32_t v = 0; v < n_views; ++v) {
+        uint64_t total = 0;
+        for (uint32_t r = 0; r < world_size; ++r) {
+            if (r == rank && offsets) offsets[v] = run + total;
+            total += all_counts[(size_t)r * n_views + v];
+        }
+        if (view_totals) view_totals[v] = total;
+        run += total;
+    }
+}
+
+}  // extern "C"

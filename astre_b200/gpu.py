@@ -1,0 +1,242 @@
+"""GpuContext: numpy-facing wrapper over the C ABI (one context = one GPU's entity shard)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import AstreError, MeshBounds, load_library
+
+FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS = 1, 2, 4, 8
+FRAME_ALL = 7
+
+PHASE_OPAQUE, PHASE_TRANSPARENT, PHASE_SHADOW_CASTER, PHASE_DEBUG = 1, 2, 4, 8
+NO_PARENT = 0xFFFFFFFF
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _arr(a, dtype, shape_tail=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape_tail is not None and a.ndim > 1:
+        assert a.shape[1:] == shape_tail, (a.shape, shape_tail)
+    return a
+
+
+def make_flags(visible, phases):
+    """Per-entity flags byte: bit0 visible, bits 1..4 RenderPhase (visual_system.cpp:32,55)."""
+    return (np.asarray(visible).astype(np.uint8) & 1) | ((np.asarray(phases).astype(np.uint8) & 15) << 1)
+
+
+class GpuContext:
+    def __init__(self, max_entities, max_views=8, max_keys=0, device=0):
+        self._lib = load_library()
+        self._h = self._lib.astre_gpu_create(int(device), int(max_entities), int(max_views), int(max_keys))
+        if not self._h:
+            raise AstreError(-1, self._lib.astre_gpu_last_error(None).decode())
+        self.max_entities = int(max_entities)
+        self.device = int(device)
+        self.n_worlds, self.views_per_world = 1, 0
+
+    # -- plumbing --
+    def _check(self, rc):
+        if rc != 0:
+            raise AstreError(rc, self._lib.astre_gpu_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.astre_gpu_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mirror --
+    def upload_entities(self, first, pos=None, rot=None, scale=None, parent=None, mesh=None, shader=None, flags=None,
+                        entity_id=None, count=None):
+        pos, rot, scale = _arr(pos, np.float32), _arr(rot, np.float32), _arr(scale, np.float32)
+        parent, mesh, shader = _arr(parent, np.uint32), _arr(mesh, np.uint32), _arr(shader, np.uint32)
+        flags, entity_id = _arr(flags, np.uint8), _arr(entity_id, np.uint64)
+        if count is None:
+            for a, per in ((pos, 3), (rot, 4), (scale, 3), (parent, 1), (mesh, 1), (shader, 1), (flags, 1), (entity_id, 1)):
+                if a is not None:
+                    count = a.size // per
+                    break
+        self._keep = (pos, rot, scale, parent, mesh, shader, flags, entity_id)
+        self._check(self._lib.astre_gpu_upload_entities(
+            self._h, int(first), int(count), _ptr(entity_id, C.c_uint64), _ptr(pos, C.c_float), _ptr(rot, C.c_float),
+            _ptr(scale, C.c_float), _ptr(parent, C.c_uint32), _ptr(mesh, C.c_uint32), _ptr(shader, C.c_uint32),
+            _ptr(flags, C.c_uint8)))
+
+    def set_entity_count(self, n):
+        self._check(self._lib.astre_gpu_set_entity_count(self._h, int(n)))
+
+    def update_trs(self, slots, pos=None, rot=None, scale=None):
+        slots = _arr(slots, np.uint32)
+        pos, rot, scale = _arr(pos, np.float32), _arr(rot, np.float32), _arr(scale, np.float32)
+        self._check(self._lib.astre_gpu_update_trs(self._h, slots.size, _ptr(slots, C.c_uint32), _ptr(pos, C.c_float),
+                                                    _ptr(rot, C.c_float), _ptr(scale, C.c_float)))
+
+    def update_trs_range(self, first, count, pos=None, rot=None, scale=None):
+        pos, rot, scale = _arr(pos, np.float32), _arr(rot, np.float32), _arr(scale, np.float32)
+        self._check(self._lib.astre_gpu_update_trs_range(self._h, int(first), int(count), _ptr(pos, C.c_float),
+                                                          _ptr(rot, C.c_float), _ptr(scale, C.c_float)))
+
+    def update_flags(self, slots, flags):
+        slots, flags = _arr(slots, np.uint32), _arr(flags, np.uint8)
+        self._check(self._lib.astre_gpu_update_flags(self._h, slots.size, _ptr(slots, C.c_uint32), _ptr(flags, C.c_uint8)))
+
+    def set_mesh_bounds(self, bounds):
+        """bounds: float array [n_meshes, 7] = center xyz, extent xyz, radius."""
+        b = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 7)
+        recs = (MeshBounds * len(b))()
+        for i, row in enumerate(b):
+            recs[i].center[:] = row[0:3].tolist()
+            recs[i].extent[:] = row[3:6].tolist()
+            recs[i].radius = float(row[6])
+        self._check(self._lib.astre_gpu_set_mesh_bounds(self._h, len(b), recs))
+
+    # -- views --
+    def set_views(self, clip, phase_masks):
+        clip = np.ascontiguousarray(clip, dtype=np.float32).reshape(-1, 16)
+        masks = np.ascontiguousarray(phase_masks, dtype=np.uint8)
+        assert len(masks) == len(clip)
+        self._check(self._lib.astre_gpu_set_views(self._h, len(clip), _ptr(clip, C.c_float), _ptr(masks, C.c_uint8)))
+        self.n_worlds, self.views_per_world = 1, len(clip)
+
+    def set_world_views(self, n_worlds, entities_per_world, clip, phase_masks):
+        masks = np.ascontiguousarray(phase_masks, dtype=np.uint8)
+        clip = np.ascontiguousarray(clip, dtype=np.float32).reshape(n_worlds, len(masks), 16)
+        self._check(self._lib.astre_gpu_set_world_views(self._h, int(n_worlds), int(entities_per_world), len(masks),
+                                                         _ptr(clip, C.c_float), _ptr(masks, C.c_uint8)))
+        self.n_worlds, self.views_per_world = int(n_worlds), len(masks)
+
+    # -- frame --
+    def frame(self, flags=FRAME_ALL, stream=None):
+        self._check(self._lib.astre_gpu_frame(self._h, int(flags), C.c_void_p(stream) if stream else None))
+
+    def sync(self):
+        self._check(self._lib.astre_gpu_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.astre_gpu_launch_count(self._h))
+
+    def last_frame_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.astre_gpu_last_frame_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def last_cull_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.astre_gpu_last_cull_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def snapshot_trs(self, stream=None):
+        self._check(self._lib.astre_gpu_snapshot_trs(self._h, C.c_void_p(stream) if stream else None))
+
+    def interpolate(self, alpha, stream=None):
+        self._check(self._lib.astre_gpu_interpolate(self._h, float(alpha), C.c_void_p(stream) if stream else None))
+
+    # -- results --
+    def read_world(self, first, count, out=None):
+        out = np.empty((count, 16), np.float32) if out is None else out
+        self._check(self._lib.astre_gpu_read_world(self._h, int(first), int(count), _ptr(out, C.c_float)))
+        return out
+
+    def read_basis(self, first, count):
+        f, u, r = (np.empty((count, 3), np.float32) for _ in range(3))
+        self._check(self._lib.astre_gpu_read_basis(self._h, int(first), int(count), _ptr(f, C.c_float),
+                                                    _ptr(u, C.c_float), _ptr(r, C.c_float)))
+        return f, u, r
+
+    def read_counts(self, out=None):
+        out = np.zeros(self.n_worlds * self.views_per_world, np.uint32) if out is None else out
+        self._check(self._lib.astre_gpu_read_counts(self._h, _ptr(out, C.c_uint32)))
+        return out
+
+    def read_total(self):
+        t = C.c_uint64()
+        self._check(self._lib.astre_gpu_read_total(self._h, C.byref(t)))
+        return t.value
+
+    def read_keys(self, view, world=0):
+        n = C.c_uint64()
+        self._check(self._lib.astre_gpu_read_keys(self._h, int(world), int(view), None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint64)
+        if n.value:
+            self._check(self._lib.astre_gpu_read_keys(self._h, int(world), int(view), _ptr(out, C.c_uint64), n.value, C.byref(n)))
+        return out
+
+    def read_all_keys(self, out=None):
+        n = C.c_uint64()
+        if out is None:
+            out = np.empty(self.read_total(), np.uint64)
+        self._check(self._lib.astre_gpu_read_all_keys(self._h, _ptr(out, C.c_uint64), out.size, C.byref(n)))
+        return out[:min(n.value, out.size)]
+
+    def read_visible_world(self, first_key, n, out=None):
+        out = np.empty((n, 16), np.float32) if out is None else out
+        self._check(self._lib.astre_gpu_read_visible_world(self._h, int(first_key), int(n), _ptr(out, C.c_float)))
+        return out
+
+    def slot_entity(self, slot):
+        e = C.c_uint64()
+        self._check(self._lib.astre_gpu_slot_entity(self._h, int(slot), C.byref(e)))
+        return e.value
+
+    def device_counts_ptr(self):
+        return self._lib.astre_gpu_device_counts(self._h)
+
+    def device_world_ptr(self):
+        return self._lib.astre_gpu_device_world(self._h)
+
+
+# ---- host-side helpers ---------------------------------------------------------
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def camera_matrices(pos, forward, up, fov_deg, aspect, z_near, z_far):
+    """CameraSystem::run's view/proj (camera_system.cpp:24-37) and clip = proj*view."""
+    lib = load_library()
+    view, proj, clip = (np.empty(16, np.float32) for _ in range(3))
+    lib.astre_camera_matrices(_f3(pos), _f3(forward), _f3(up), fov_deg, aspect, z_near, z_far,
+                              _ptr(view, C.c_float), _ptr(proj, C.c_float), _ptr(clip, C.c_float))
+    return view, proj, clip
+
+
+def light_space_matrix(pos, direction, light_type, outer_cutoff=0.0):
+    lib = load_library()
+    clip = np.empty(16, np.float32)
+    ok = lib.astre_light_space_matrix(_f3(pos), _f3(direction), int(light_type), float(outer_cutoff), _ptr(clip, C.c_float))
+    return clip if ok else None
+
+
+def ortho_view_matrix(eye, center, up, l, r, b, t, n, f):
+    lib = load_library()
+    clip = np.empty(16, np.float32)
+    lib.astre_ortho_view_matrix(_f3(eye), _f3(center), _f3(up), l, r, b, t, n, f, _ptr(clip, C.c_float))
+    return clip
+
+
+def global_offsets(all_counts, rank):
+    """all_counts [world_size, n_views] -> (offsets[n_views] of this rank, totals[n_views])."""
+    lib = load_library()
+    a = np.ascontiguousarray(all_counts, dtype=np.uint32)
+    ws, nv = a.shape
+    off, tot = np.zeros(nv, np.uint64), np.zeros(nv, np.uint64)
+    lib.astre_global_offsets(_ptr(a, C.c_uint32), ws, int(rank), nv, _ptr(off, C.c_uint64), _ptr(tot, C.c_uint64))
+    return off, tot

@@ -1,0 +1,231 @@
+/*
+ * astre_gpu.h -- C ABI of the B200-native transform + visibility path for the
+ * Astre engine (libastre_gpu.so, sm_100a).
+ *
+ * The reference engine has no FFI / plugin seam for this path;
+ * each entry point below cites the reference interface it replaces, relative to
+ * the reference root.  Path shorthand: ECS/, Render/, Pipeline/, Math/, Loader/
+ * are under engine/modules/.
+ *
+ * Contract
+ *   - opaque context, int status returns (ASTRE_OK == 0), no exceptions, no
+ *     torch / C++ types in any signature;
+ *   - caller-owned host buffers (pinned memory makes the copies asynchronous),
+ *     library-owned device buffers;
+ *   - all calls on one context come from one thread at a time, which matches
+ *     "exactly one TransformSystem::run in flight" (Pipeline/src/logic_pipelines.cpp:30-33);
+ *   - there is no CPU fallback: without a CUDA device astre_gpu_create returns NULL
+ *     and astre_gpu_last_error(NULL) says why.
+ *
+ * Layout conventions (same as the reference): mat4 is 16 floats, column-major,
+ * m[c*4+r] == glm M[c][r] (Math/src/math.cpp:70-93); quaternions are x,y,z,w
+ * (Math/src/math.cpp:124-133); vec3 arrays are packed xyz.
+ */
+#ifndef ASTRE_GPU_H
+#define ASTRE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ASTRE_API __attribute__((visibility("default")))
+#else
+#define ASTRE_API
+#endif
+
+typedef struct astre_gpu_ctx astre_gpu_ctx;
+
+enum {
+    ASTRE_OK            = 0,
+    ASTRE_ERR_INVALID   = 1,  /* bad argument (range, alignment, null)            */
+    ASTRE_ERR_CUDA      = 2,  /* a CUDA call failed; see astre_gpu_last_error     */
+    ASTRE_ERR_CAPACITY  = 3,  /* more visible keys than max_keys; lists truncated */
+    ASTRE_ERR_HIERARCHY = 4,  /* parent index out of range or cyclic              */
+    ASTRE_ERR_STATE     = 5   /* call made before its prerequisites               */
+};
+
+/* RenderPhase bits, Render/include/render/render.hpp:29-36 */
+enum {
+    ASTRE_PHASE_OPAQUE        = 1u << 0,
+    ASTRE_PHASE_TRANSPARENT   = 1u << 1,
+    ASTRE_PHASE_SHADOW_CASTER = 1u << 2,
+    ASTRE_PHASE_DEBUG         = 1u << 3
+};
+
+/* Per-entity flags byte: bit0 = VisualComponent.visible
+ * (Proto/ECS/components/visual_component.proto:9, ECS/src/system/visual_system.cpp:32),
+ * bits 1..4 = RenderProxy.phases (visual_system.cpp:55).  An entity for which
+ * VisualSystem would emit no proxy (no Visual component, unresolved mesh or
+ * shader name -- visual_system.cpp:26-30) is uploaded with phases == 0. */
+#define ASTRE_FLAG_VISIBLE        0x01u
+#define ASTRE_FLAGS(visible, phases) ((uint8_t)(((visible) ? 1u : 0u) | (((phases) & 15u) << 1)))
+
+#define ASTRE_NO_PARENT 0xFFFFFFFFu
+
+/* frame stages */
+enum {
+    ASTRE_FRAME_TRANSFORM = 1u << 0,  /* TransformSystem::run matrices (always implied)     */
+    ASTRE_FRAME_CULL      = 1u << 1,  /* frustum test + compaction + key emission            */
+    ASTRE_FRAME_SORT      = 1u << 2,  /* device radix sort of the emitted keys               */
+    ASTRE_FRAME_BASIS     = 1u << 3,  /* forward/up/right of every entity                    */
+    ASTRE_FRAME_ALL       = 7u
+};
+
+/* Local-space bounds of one mesh: a box of half extents `extent` around
+ * `center`, inflated by `radius` (AABB: radius 0; sphere: extent 0).
+ * Spec-defined -- the reference keeps no bounds. */
+typedef struct {
+    float center[3];
+    float extent[3];
+    float radius;
+    uint32_t reserved;
+} astre_mesh_bounds;
+
+/* Draw key, ascending = draw order (spec-defined):
+ *   world(Wb) | view(5) | shader(8) | mesh(11) | depth(14) | local slot(26-Wb)
+ * Wb = ceil(log2(n_worlds)) (0 for a single world, which gives
+ * view[63:59] shader[58:51] mesh[50:40] depth[39:26] slot[25:0]). */
+#define ASTRE_KEY_SLOT_BITS   26
+#define ASTRE_KEY_DEPTH_BITS  14
+#define ASTRE_KEY_MESH_BITS   11
+#define ASTRE_KEY_SHADER_BITS 8
+#define ASTRE_KEY_VIEW_BITS   5
+#define ASTRE_MAX_VIEWS       32
+
+/* ---- lifetime ------------------------------------------------------------- */
+
+/* Replaces the Registry + ComponentStorage<T> hash maps as the iteration source
+ * (ECS/include/ecs/registry.hpp:81-91, ECS/include/ecs/component_manager.hpp:34-90):
+ * a dense slot <-> entity mirror in device structure-of-arrays buffers.
+ * max_keys == 0 means max_entities * max_views. */
+ASTRE_API astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_views, uint64_t max_keys);
+ASTRE_API void astre_gpu_destroy(astre_gpu_ctx *ctx);
+/* Last error text of ctx, or of the last failed astre_gpu_create when ctx is NULL. */
+ASTRE_API const char *astre_gpu_last_error(const astre_gpu_ctx *ctx);
+ASTRE_API const char *astre_gpu_version(void);
+
+/* ---- mirror maintenance --------------------------------------------------- */
+
+/* Spawn / full refresh of slots [first, first+count): what EntityLoader::load ->
+ * Registry::addComponent feeds the component storages (Loader/src/entity_loader.cpp:11-76).
+ * Null pos3/rot4/scale3 take TransformSystem's defaults (transform_system.cpp:24-49:
+ * position 0, rotation w=1, scale 1).  parent_slot may be NULL (all roots);
+ * entity_id may be NULL (id == slot).  mesh_id < 2048, shader_id < 256. */
+ASTRE_API int astre_gpu_upload_entities(astre_gpu_ctx *ctx, uint32_t first, uint32_t count,
+                                        const uint64_t *entity_id,
+                                        const float *pos3, const float *rot_xyzw4, const float *scale3,
+                                        const uint32_t *parent_slot,
+                                        const uint32_t *mesh_id, const uint32_t *shader_id,
+                                        const uint8_t *flags);
+/* Number of live slots becomes n (slots >= n are ignored by frames). */
+ASTRE_API int astre_gpu_set_entity_count(astre_gpu_ctx *ctx, uint32_t n);
+
+/* Dirty-set update of position/rotation/scale: the writes ScriptSystem / Lua
+ * bindings make between ticks (ECS/src/system/script_system.cpp:31-35,
+ * Script/include/script/component_binding.hpp:26-115).  Any of the three arrays
+ * may be NULL (left unchanged). */
+ASTRE_API int astre_gpu_update_trs(astre_gpu_ctx *ctx, uint32_t n, const uint32_t *slots,
+                                   const float *pos3, const float *rot_xyzw4, const float *scale3);
+/* Same for a contiguous slot range (no index list). */
+ASTRE_API int astre_gpu_update_trs_range(astre_gpu_ctx *ctx, uint32_t first, uint32_t count,
+                                         const float *pos3, const float *rot_xyzw4, const float *scale3);
+/* VisualComponent.visible / phases changes. */
+ASTRE_API int astre_gpu_update_flags(astre_gpu_ctx *ctx, uint32_t n, const uint32_t *slots, const uint8_t *flags);
+
+ASTRE_API int astre_gpu_set_mesh_bounds(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre_mesh_bounds *bounds);
+
+/* ---- views ---------------------------------------------------------------- */
+
+/* One clip matrix (proj*view, column-major) and one RenderPhase mask per view:
+ * view 0 is normally the camera (CameraSystem::run, ECS/src/system/camera_system.cpp:24-37,
+ * mask Opaque -- Pipeline/src/deferred_shading.cpp:117-120), views 1.. the shadow
+ * casters (calculateLightSpaceMatrices, ECS/src/system/light_system.cpp:105-160,
+ * mask ShadowCaster -- deferred_shading.cpp:153-156). */
+ASTRE_API int astre_gpu_set_views(astre_gpu_ctx *ctx, uint32_t n_views,
+                                  const float *clip_colmajor16, const uint8_t *phase_mask_per_view);
+/* Batched independent worlds: world w owns slots [w*entities_per_world,
+ * (w+1)*entities_per_world) and has its own views_per_world clip matrices
+ * (clip layout [world][view][16], masks [view]).  entities_per_world % 4 == 0. */
+ASTRE_API int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t entities_per_world,
+                                        uint32_t views_per_world,
+                                        const float *clip_colmajor16, const uint8_t *phase_mask_per_view);
+
+/* ---- the frame ------------------------------------------------------------ */
+
+/* TransformSystem::run + VisualSystem::run + the per-pass filters of
+ * deferredShadingStage in one enqueue (transform_system.cpp:11-70,
+ * visual_system.cpp:14-61, deferred_shading.cpp:115-121,145-161).
+ * stream: a cudaStream_t cast to void* (NULL = the context's own stream).
+ * Asynchronous; results are read with the astre_gpu_read_* calls, which
+ * synchronise. */
+ASTRE_API int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream);
+ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
+/* Number of kernel launches the library has enqueued on this context so far. */
+ASTRE_API uint64_t astre_gpu_launch_count(const astre_gpu_ctx *ctx);
+/* Duration in ms of the most recent astre_gpu_frame, measured with CUDA events
+ * on the launching stream (synchronises). */
+ASTRE_API int astre_gpu_last_frame_ms(astre_gpu_ctx *ctx, float *ms);
+/* Same, for the transform+cull kernels only (the dominant kernel). */
+ASTRE_API int astre_gpu_last_cull_ms(astre_gpu_ctx *ctx, float *ms);
+
+/* f1: interpolateFrame's per-proxy step (Render/src/render.cpp:26-39): the TRS of
+ * the previous tick is kept on the device by astre_gpu_snapshot_trs; this writes
+ * translate(mix(p)) * toMat4(slerp(q)) * scale(mix(s)) into the world buffer. */
+ASTRE_API int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream);
+ASTRE_API int astre_gpu_interpolate(astre_gpu_ctx *ctx, float alpha, void *stream);
+
+/* ---- results -------------------------------------------------------------- */
+
+/* transform_matrix of slots [first, first+count) (TransformComponent field 7). */
+ASTRE_API int astre_gpu_read_world(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, float *mat4_colmajor);
+/* forward / up / right of slots [first, first+count) (fields 4,6,5); needs ASTRE_FRAME_BASIS. */
+ASTRE_API int astre_gpu_read_basis(astre_gpu_ctx *ctx, uint32_t first, uint32_t count,
+                                   float *forward3, float *up3, float *right3);
+/* counts[world*views_per_world + view].  Returns ASTRE_ERR_CAPACITY (after filling
+ * counts) if the frame produced more keys than max_keys. */
+ASTRE_API int astre_gpu_read_counts(astre_gpu_ctx *ctx, uint32_t *counts);
+/* Total number of keys of the last frame. */
+ASTRE_API int astre_gpu_read_total(astre_gpu_ctx *ctx, uint64_t *total);
+/* The sorted draw list of (world, view): up to cap keys, *n_out = its length. */
+ASTRE_API int astre_gpu_read_keys(astre_gpu_ctx *ctx, uint32_t world, uint32_t view,
+                                  uint64_t *keys, uint64_t cap, uint64_t *n_out);
+/* The whole key buffer (all worlds and views; sorted iff ASTRE_FRAME_SORT ran). */
+ASTRE_API int astre_gpu_read_all_keys(astre_gpu_ctx *ctx, uint64_t *keys, uint64_t cap, uint64_t *n_out);
+/* World matrices of the first n keys of the sorted list, in list order (what
+ * VisualSystem copies into RenderProxy.inputs["uModel"], visual_system.cpp:47). */
+ASTRE_API int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_t n, float *mat4_colmajor);
+/* Entity id of a slot (the id given at upload). */
+ASTRE_API int astre_gpu_slot_entity(const astre_gpu_ctx *ctx, uint32_t slot, uint64_t *entity_id);
+
+/* Device pointers for zero-copy consumers (CUDA-GL interop, NCCL exchange of
+ * counts).  Valid until astre_gpu_destroy. */
+ASTRE_API void *astre_gpu_device_world(astre_gpu_ctx *ctx);        /* float[max_entities][16] */
+ASTRE_API void *astre_gpu_device_counts(astre_gpu_ctx *ctx);       /* uint32[n_worlds*views]   */
+ASTRE_API void *astre_gpu_device_sorted_keys(astre_gpu_ctx *ctx);  /* uint64[]; synchronises  */
+
+/* ---- host-side helpers (no device work) ------------------------------------ */
+
+/* CameraSystem::run's matrices (camera_system.cpp:24-37): view = lookAt(pos, pos+forward, up),
+ * proj = perspective(radians(fov_deg), aspect, near, far); clip = proj*view. */
+ASTRE_API void astre_camera_matrices(const float *pos3, const float *forward3, const float *up3,
+                                     float fov_deg, float aspect, float z_near, float z_far,
+                                     float *view16, float *proj16, float *clip16);
+/* calculateLightSpaceMatrices for one light (light_system.cpp:105-160);
+ * type 1 directional, 2 point, 3 spot.  Returns 0 for an unknown type. */
+ASTRE_API int astre_light_space_matrix(const float *pos3, const float *dir3, int type, float outer_cutoff, float *clip16);
+/* lookAt + ortho clip matrix, for cascade-style shadow frusta. */
+ASTRE_API void astre_ortho_view_matrix(const float *eye3, const float *center3, const float *up3,
+                                       float l, float r, float b, float t, float n, float f, float *clip16);
+/* Exclusive scan over (view, rank) of all ranks' per-view counts: offset of
+ * this rank's segment of each view in the global draw list.
+ * all_counts is [world_size][n_views]; offsets/view_totals are [n_views]. */
+ASTRE_API void astre_global_offsets(const uint32_t *all_counts, uint32_t world_size, uint32_t rank,
+                                    uint32_t n_views, uint64_t *offsets, uint64_t *view_totals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTRE_GPU_H */

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Bit-exact:
+world matrices (0 ULP, NaN payloads aside), per-view counts and sorted draw keys."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from astre_b200 import AstreError, GpuContext, gpu, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def run_scene(scene, flags=gpu.FRAME_ALL, max_keys=0):
+    with GpuContext(max(scene.n, 1), max_views=max(scene.views_per_world, 1), max_keys=max_keys) as ctx:
+        scenes.load_into(ctx, scene)
+        ctx.frame(flags)
+        world = ctx.read_world(0, scene.n)
+        counts = ctx.read_counts()
+        keys = ctx.read_all_keys()
+        per_view = [[ctx.read_keys(v, w) for v in range(scene.views_per_world)] for w in range(scene.n_worlds)] \
+            if scene.n_worlds * scene.views_per_world <= 64 else None
+        return world, counts, keys, per_view
+
+
+def check_scene(oracle, scene):
+    o_world, o_keys, o_counts = oracle.frame(scene)
+    world, counts, keys, per_view = run_scene(scene)
+    assert np.array_equal(oracle_lib.bits(world), oracle_lib.bits(o_world)), \
+        f"world matrices differ: max ulp {oracle_lib.ulp_diff(world, o_world).max()}"
+    assert np.array_equal(counts, o_counts)
+    assert np.array_equal(keys, o_keys)
+    if per_view is not None:
+        flat = np.concatenate([k for w in per_view for k in w]) if len(o_keys) else np.empty(0, np.uint64)
+        assert np.array_equal(flat, o_keys)
+    return len(o_keys)
+
+
+def test_config1_flat_10k(oracle):
+    assert check_scene(oracle, scenes.config1()) > 0
+
+
+@pytest.mark.parametrize("n", [1, 3, 127, 128, 129, 1023, 1024, 1025, 4099])
+def test_ragged_sizes(oracle, n):
+    check_scene(oracle, scenes.config1(n))
+
+
+def test_config2_hierarchy_small(oracle):
+    check_scene(oracle, scenes.config2(n=65_536 + 13))
+
+
+def test_config2_hierarchy_1m(oracle):
+    assert check_scene(oracle, scenes.config2()) > 0
+
+
+def test_hierarchy_arbitrary_slot_order(oracle):
+    """Levels that are not contiguous slot ranges take the indexed kernel."""
+    s = scenes.config2(n=20_000)
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(s.n).astype(np.uint32)      # new slot of old entity i = perm[i]
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(s.n, dtype=np.uint32)
+    for name in ("pos", "rot", "scale", "mesh", "shader", "flags"):
+        setattr(s, name, np.ascontiguousarray(getattr(s, name)[inv]))
+    old_parent = s.parent[inv]
+    s.parent = np.where(old_parent == gpu.NO_PARENT, gpu.NO_PARENT, perm[np.minimum(old_parent, s.n - 1)]).astype(np.uint32)
+    check_scene(oracle, s)
+
+
+def test_config3_five_views_1m(oracle):
+    assert check_scene(oracle, scenes.config3(1 << 20)) > 0
+
+
+def test_config3_full_16m(oracle):
+    """BASELINE.json's headline configuration at full size."""
+    s = scenes.config3()
+    n_keys = check_scene(oracle, s)
+    assert n_keys > 100_000
+
+
+def test_config5_worlds(oracle):
+    s = scenes.config5(n_worlds=24, entities_per_world=4096)
+    assert check_scene(oracle, s) > 0
+
+
+def test_all_visible_multi_tile_sort(oracle):
+    """Every entity inside every view: exercises compaction at full rate and a
+    multi-tile sort with all eight digit passes live in the low bits."""
+    s = scenes.config1(300_000)
+    s.pos = (s.pos * np.float32(0.02)).astype(np.float32)
+    s.pos[:, 2] -= np.float32(40.0)
+    s.flags[:] = gpu.make_flags(np.ones(s.n, bool), np.full(s.n, 5, np.uint8))
+    s.clip = np.repeat(s.clip, 3, axis=1)
+    s.masks = np.array([1, 4, 1], np.uint8)
+    n_keys = check_scene(oracle, s)
+    assert n_keys > 2 * s.n
+
+
+def test_edge_values_bit_exact(oracle):
+    """-0, denormals, Inf, NaN, negative and zero scale, un-normalised and zero quaternions."""
+    s = scenes.config1(4096)
+    specials = np.array([0.0, -0.0, 1.0, -1.0, 1e-42, -1e-42, 3e38, -3e38, np.inf, -np.inf, np.nan,
+                         0.70710678, -0.70710678, 0.5, -0.5, 2.0], np.float32)
+    rng = np.random.default_rng(11)
+    for arr in (s.pos, s.rot, s.scale):
+        pick = rng.random(arr.shape) < 0.35
+        arr[pick] = specials[rng.integers(0, len(specials), pick.sum())]
+    # axis-aligned rotations with negative components and mirrored scales: the -0 cases
+    s.rot[:64] = 0
+    s.rot[:64, 1] = np.float32(-0.70710678)
+    s.rot[:64, 3] = np.float32(0.70710678)
+    s.scale[:64:2, 0] = np.float32(-1.0)
+    check_scene(oracle, s)
+
+
+def test_invisible_and_phase_masks(oracle):
+    s = scenes.config3(50_000)
+    s.pos = (s.pos * np.float32(0.01)).astype(np.float32)
+    s.pos[:, 2] -= np.float32(30.0)
+    vis = (np.arange(s.n) % 3) != 0
+    phases = (np.arange(s.n) % 16).astype(np.uint8)
+    s.flags = gpu.make_flags(vis, phases)
+    s.mesh[::7] = 2000        # beyond the bounds table: never drawn
+    check_scene(oracle, s)
+
+
+def test_no_views_transform_only(oracle):
+    s = scenes.config1(5000)
+    with GpuContext(s.n, max_views=4) as ctx:
+        ctx.upload_entities(0, s.pos, s.rot, s.scale, None, s.mesh, s.shader, s.flags)
+        ctx.frame(gpu.FRAME_TRANSFORM)
+        world = ctx.read_world(0, s.n)
+        assert ctx.read_total() == 0
+    assert np.array_equal(oracle_lib.bits(world), oracle_lib.bits(oracle.transform_flat(s.pos, s.rot, s.scale)))
+
+
+def test_defaults_when_components_absent(oracle):
+    """has_position/has_rotation/has_scale == false -> 0 / identity / 1 (transform_system.cpp:24-49)."""
+    n = 100
+    with GpuContext(n) as ctx:
+        ctx.upload_entities(0, count=n)
+        ctx.frame(gpu.FRAME_TRANSFORM)
+        world = ctx.read_world(0, n)
+    assert np.array_equal(world, np.tile(np.eye(4, dtype=np.float32).reshape(-1), (n, 1)))
+
+
+def test_basis_vectors(oracle):
+    s = scenes.config1(10_000)
+    with GpuContext(s.n) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame(gpu.FRAME_ALL | gpu.FRAME_BASIS)
+        f, u, r = ctx.read_basis(0, s.n)
+    _, of, ou, orr = oracle.transform_flat(s.pos, s.rot, s.scale, basis=True)
+    for a, b in ((f, of), (u, ou), (r, orr)):
+        assert np.array_equal(oracle_lib.bits(a), oracle_lib.bits(b))
+
+
+def test_dirty_updates(oracle):
+    s = scenes.config1(20_000)
+    with GpuContext(s.n) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        rng = np.random.default_rng(3)
+        slots = rng.choice(s.n, 777, replace=False).astype(np.uint32)
+        s.pos[slots] = (rng.random((777, 3), np.float32) * 20 - 10).astype(np.float32)
+        s.rot[slots[:100]] = np.array([0, 0, 0, 1], np.float32)
+        ctx.update_trs(slots, pos=s.pos[slots])
+        ctx.update_trs(slots[:100], rot=s.rot[slots[:100]])
+        lo, cnt = 5000, 3000
+        s.scale[lo:lo + cnt] *= np.float32(1.5)
+        ctx.update_trs_range(lo, cnt, scale=s.scale[lo:lo + cnt])
+        fl_slots = np.arange(0, s.n, 5, dtype=np.uint32)
+        s.flags[fl_slots] = gpu.make_flags(np.zeros(len(fl_slots), bool), np.full(len(fl_slots), 5, np.uint8))
+        ctx.update_flags(fl_slots, s.flags[fl_slots])
+        ctx.frame()
+        world, counts, keys = ctx.read_world(0, s.n), ctx.read_counts(), ctx.read_all_keys()
+    o_world, o_keys, o_counts = oracle.frame(s)
+    assert np.array_equal(oracle_lib.bits(world), oracle_lib.bits(o_world))
+    assert np.array_equal(counts, o_counts) and np.array_equal(keys, o_keys)
+
+
+def test_visible_world_gather(oracle):
+    s = scenes.config1()
+    with GpuContext(s.n) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        keys = ctx.read_all_keys()
+        vis = ctx.read_visible_world(0, len(keys))
+        world = ctx.read_world(0, s.n)
+    slots = (keys & np.uint64((1 << 26) - 1)).astype(np.int64)
+    assert np.array_equal(oracle_lib.bits(vis), oracle_lib.bits(world[slots]))
+
+
+def test_capacity_overflow_is_reported():
+    s = scenes.config1(50_000)
+    s.pos = (s.pos * np.float32(0.01)).astype(np.float32)
+    s.pos[:, 2] -= np.float32(30.0)
+    with GpuContext(s.n, max_views=1, max_keys=1000) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        with pytest.raises(AstreError) as e:
+            ctx.read_counts()
+        assert e.value.code == 3
+
+
+def test_bad_hierarchy_is_rejected():
+    n = 16
+    parent = np.full(n, gpu.NO_PARENT, np.uint32)
+    parent[3], parent[4] = 4, 3      # cycle
+    with GpuContext(n) as ctx:
+        ctx.upload_entities(0, parent=parent, count=n)
+        with pytest.raises(AstreError) as e:
+            ctx.frame()
+        assert e.value.code == 4
+
+
+def test_repeated_frames_are_identical(oracle):
+    s = scenes.config3(200_000)
+    with GpuContext(s.n, max_views=5) as ctx:
+        scenes.load_into(ctx, s)
+        ref = None
+        for _ in range(5):
+            ctx.frame()
+            k = ctx.read_all_keys().copy()
+            if ref is None:
+                ref = k
+            assert np.array_equal(k, ref)
+    assert np.array_equal(ref, oracle.frame(s)[1])
