@@ -39,7 +39,8 @@ struct astre_gpu_ctx {
     uint32_t max_entities = 0, cap_entities = 0, max_views = 0;
     uint64_t max_keys = 0;
     uint32_t n_entities = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream in use (own_stream unless astre_gpu_set_stream)
+    cudaStream_t own_stream = nullptr;
 
     // mirror
     float *d_planes = nullptr;       // 10 planes of cap_entities floats
@@ -340,7 +341,8 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     };
 #define CKC(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) return bail(#call, e2_); } while (0)
     const size_t cap = ctx->cap_entities;
-    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
     CKC(cudaMalloc(&ctx->d_planes, cap * 10 * sizeof(float)));
     CKC(cudaMemset(ctx->d_planes, 0, cap * 10 * sizeof(float)));
     CKC(cudaMalloc(&ctx->d_meta, cap * sizeof(uint32_t)));
@@ -393,7 +395,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -688,6 +690,14 @@ int astre_gpu_sync(astre_gpu_ctx *ctx)
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_stream(astre_gpu_ctx *ctx, void *stream)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
     return ASTRE_OK;
 }
 

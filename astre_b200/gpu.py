@@ -129,6 +129,10 @@ class GpuContext:
     def sync(self):
         self._check(self._lib.astre_gpu_sync(self._h))
 
+    def set_stream(self, stream):
+        """stream: a cudaStream_t handle as int (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self._check(self._lib.astre_gpu_set_stream(self._h, C.c_void_p(stream) if stream else None))
+
     @property
     def launch_count(self):
         return int(self._lib.astre_gpu_launch_count(self._h))

@@ -163,6 +163,10 @@ ASTRE_API int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, u
  * synchronise. */
 ASTRE_API int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream);
 ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
+/* Makes every later call on ctx (mirror updates, frames with stream == NULL,
+ * read-backs) enqueue on the caller's cudaStream_t instead of the context's own
+ * stream; NULL restores the internal stream.  Synchronises the old stream. */
+ASTRE_API int astre_gpu_set_stream(astre_gpu_ctx *ctx, void *stream);
 /* Number of kernel launches the library has enqueued on this context so far. */
 ASTRE_API uint64_t astre_gpu_launch_count(const astre_gpu_ctx *ctx);
 /* Duration in ms of the most recent astre_gpu_frame, measured with CUDA events
