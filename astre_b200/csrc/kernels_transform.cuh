@@ -91,7 +91,7 @@ __device__ __forceinline__ float4 ld_stream(const float *p)
     return __ldcs(reinterpret_cast<const float4 *>(p));
 }
 
-// World-space bounds (spec; mirrored by oracle world_bounds_of).
+// World-space bounds (spec; mirrored by the CPU checker).
 struct WorldBounds { float cx, cy, cz, ex, ey, ez, r; };
 
 __device__ __forceinline__ WorldBounds world_bounds(const float (&m)[16], const BoundsDev &b)

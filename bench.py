@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="astre_b200")
-    ap.add_argument("--entities", type=int, default=N_PER_GPU, help=argparse.SUPPRESS)
+    ap.add_argument("--entities", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -183,8 +183,8 @@ def main():
     import torch.distributed as dist
     from astre_b200 import GpuContext, gpu, scenes
 
-    global N_PER_GPU
-    N_PER_GPU = args.entities
+    if args.entities:
+        globals()["N_PER_GPU"] = args.entities
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +199,11 @@ def main():
     n = scene.n
     ctx = GpuContext(n, max_views=F, device=local_rank)
     scenes.load_into(ctx, scene)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library enqueues everything on it and the
+    # torch events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     counts_dev = torch.zeros(F, dtype=torch.int32, device="cuda")
