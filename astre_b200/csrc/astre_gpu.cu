@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -15,6 +16,7 @@
 #include "kernels_mirror.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_transform.cuh"
+#include "kernels_fused.cuh"
 
 using namespace astre;
 
@@ -43,9 +45,8 @@ struct astre_gpu_ctx {
     cudaStream_t own_stream = nullptr;
 
     // mirror
-    float *d_planes = nullptr;       // 10 planes of cap_entities floats
-    float *d_prev = nullptr;         // previous-tick TRS planes (lazy; interpolation)
-    uint32_t *d_meta = nullptr, *d_parent = nullptr;
+    float *d_tiles = nullptr;        // tile-major mirror: cap_entities/128 records of 1536 words
+    float *d_prev = nullptr;         // previous-tick copy of the mirror (lazy; interpolation)
     float4 *d_world = nullptr;
     float *d_basis = nullptr;        // fwd3 | up3 | right3, packed (lazy)
     BoundsDev *d_bounds = nullptr;
@@ -90,11 +91,11 @@ struct astre_gpu_ctx {
     cudaEvent_t ev_begin = nullptr, ev_cull0 = nullptr, ev_cull1 = nullptr, ev_end = nullptr;
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
-    int cull_blocks_per_sm = 2;
+    int fused_blocks_per_sm = 2;
+    ViewSet h_viewset;               // single-world view records, passed as a kernel parameter
     std::string err;
 
-    float *plane(int i) const { return d_planes + (size_t)i * cap_entities; }
-    float *prev(int i) const { return d_prev + (size_t)i * cap_entities; }
+    size_t tile_words() const { return (size_t)(cap_entities / kWarpTile) * kTileFloats; }
 };
 
 namespace {
@@ -129,23 +130,10 @@ int fail(astre_gpu_ctx *ctx, int code, const char *fmt, ...)
 
 inline uint32_t ceil_div(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
-Planes planes_of(const astre_gpu_ctx *c)
-{
-    Planes p;
-    p.px = c->plane(0); p.py = c->plane(1); p.pz = c->plane(2);
-    p.qx = c->plane(3); p.qy = c->plane(4); p.qz = c->plane(5); p.qw = c->plane(6);
-    p.sx = c->plane(7); p.sy = c->plane(8); p.sz = c->plane(9);
-    return p;
-}
-
 FrameParams params_of(const astre_gpu_ctx *c, bool cull)
 {
     FrameParams P;
-    P.px = c->plane(0); P.py = c->plane(1); P.pz = c->plane(2);
-    P.qx = c->plane(3); P.qy = c->plane(4); P.qz = c->plane(5); P.qw = c->plane(6);
-    P.sx = c->plane(7); P.sy = c->plane(8); P.sz = c->plane(9);
-    P.meta = c->d_meta;
-    P.parent = c->d_parent;
+    P.tiles = c->d_tiles;
     P.world = c->d_world;
     P.bounds = c->d_bounds;
     P.views = c->d_views;
@@ -343,12 +331,10 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     const size_t cap = ctx->cap_entities;
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    CKC(cudaMalloc(&ctx->d_planes, cap * 10 * sizeof(float)));
-    CKC(cudaMemset(ctx->d_planes, 0, cap * 10 * sizeof(float)));
-    CKC(cudaMalloc(&ctx->d_meta, cap * sizeof(uint32_t)));
-    CKC(cudaMemset(ctx->d_meta, 0, cap * sizeof(uint32_t)));
-    CKC(cudaMalloc(&ctx->d_parent, cap * sizeof(uint32_t)));
-    CKC(cudaMemset(ctx->d_parent, 0xFF, cap * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_tiles, ctx->tile_words() * sizeof(float)));
+    CKC(cudaMemset(ctx->d_tiles, 0, ctx->tile_words() * sizeof(float)));
+    k_init_tiles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_tiles, ctx->cap_entities);
+    CKC(cudaGetLastError());
     CKC(cudaMalloc(&ctx->d_world, cap * 4 * sizeof(float4)));
     ctx->cap_meshes = 16;
     CKC(cudaMalloc(&ctx->d_bounds, ctx->cap_meshes * sizeof(BoundsDev)));
@@ -372,12 +358,16 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaEventCreate(&ctx->ev_cull0));
     CKC(cudaEventCreate(&ctx->ev_cull1));
     CKC(cudaEventCreate(&ctx->ev_end));
-    const int stage_bytes = kWarpsPerBlock * kStageF4PerWarp * (int)sizeof(float4);
-    CKC(cudaFuncSetAttribute(k_transform_cull<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
-    CKC(cudaFuncSetAttribute(k_transform_cull<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
     int occ = 0;
-    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_transform_cull<false>, kBlockThreads, stage_bytes));
-    ctx->cull_blocks_per_sm = std::max(occ, 1);
+    CKC(cudaFuncSetAttribute(k_frame_fused<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaFuncSetAttribute(k_frame_fused<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaFuncSetAttribute(k_frame_fused<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaFuncSetAttribute(k_frame_fused<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaFuncSetAttribute(k_frame_fused<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaFuncSetAttribute(k_frame_fused<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frame_fused<false, false, true>, kBlockThreads, kFusedSmemBytes));
+    ctx->fused_blocks_per_sm = std::max(occ, 1);
+    std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     CKC(cudaDeviceSynchronize());
 #undef CKC
     ctx->h_parent.assign(max_entities, ASTRE_NO_PARENT);
@@ -389,7 +379,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = { ctx->d_planes, ctx->d_prev, ctx->d_meta, ctx->d_parent, ctx->d_world, ctx->d_basis, ctx->d_bounds,
+    void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
                      ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -418,7 +408,6 @@ int astre_gpu_upload_entities(astre_gpu_ctx *ctx, uint32_t first, uint32_t count
     CK(cudaSetDevice(ctx->device));
     if (int rc = ensure_stage(ctx)) return rc;
     cudaStream_t s = ctx->stream;
-    const Planes pl = planes_of(ctx);
     for (uint32_t done = 0; done < count;) {
         const uint32_t c = std::min(ctx->stage_entities, count - done);
         unsigned char *st = ctx->d_stage;
@@ -438,10 +427,10 @@ int astre_gpu_upload_entities(astre_gpu_ctx *ctx, uint32_t first, uint32_t count
         if (parent_slot) CK(cudaMemcpyAsync(d_par, parent_slot + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
         if (flags) CK(cudaMemcpyAsync(d_flags, flags + done, (size_t)c, cudaMemcpyHostToDevice, s));
         const uint32_t grid = std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8);
-        k_ingest_trs<<<grid, 256, 0, s>>>(pl, nullptr, first + done, c, pos3 ? d_pos : nullptr, rot4 ? d_rot : nullptr,
+        k_ingest_trs<<<grid, 256, 0, s>>>(ctx->d_tiles, nullptr, first + done, c, pos3 ? d_pos : nullptr, rot4 ? d_rot : nullptr,
                                           scl3 ? d_scl : nullptr, true);
         CK_LAUNCH();
-        k_ingest_meta<<<grid, 256, 0, s>>>(ctx->d_meta, ctx->d_parent, first + done, c, mesh_id ? d_mesh : nullptr,
+        k_ingest_meta<<<grid, 256, 0, s>>>(ctx->d_tiles, first + done, c, mesh_id ? d_mesh : nullptr,
                                            shader_id ? d_shader : nullptr, flags ? d_flags : nullptr,
                                            parent_slot ? d_par : nullptr);
         CK_LAUNCH();
@@ -467,7 +456,6 @@ static int update_trs_impl(astre_gpu_ctx *ctx, const uint32_t *slots, uint32_t f
     CK(cudaSetDevice(ctx->device));
     if (int rc = ensure_stage(ctx)) return rc;
     cudaStream_t s = ctx->stream;
-    const Planes pl = planes_of(ctx);
     for (uint32_t done = 0; done < n;) {
         const uint32_t c = std::min(ctx->stage_entities, n - done);
         unsigned char *st = ctx->d_stage;
@@ -481,7 +469,7 @@ static int update_trs_impl(astre_gpu_ctx *ctx, const uint32_t *slots, uint32_t f
         if (rot4) CK(cudaMemcpyAsync(d_rot, rot4 + 4 * (size_t)done, (size_t)c * 16, cudaMemcpyHostToDevice, s));
         if (scl3) CK(cudaMemcpyAsync(d_scl, scl3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
         const uint32_t grid = std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8);
-        k_ingest_trs<<<grid, 256, 0, s>>>(pl, slots ? d_slots : nullptr, first + done, c, pos3 ? d_pos : nullptr,
+        k_ingest_trs<<<grid, 256, 0, s>>>(ctx->d_tiles, slots ? d_slots : nullptr, first + done, c, pos3 ? d_pos : nullptr,
                                           rot4 ? d_rot : nullptr, scl3 ? d_scl : nullptr, false);
         CK_LAUNCH();
         done += c;
@@ -521,7 +509,7 @@ int astre_gpu_update_flags(astre_gpu_ctx *ctx, uint32_t n, const uint32_t *slots
         uint8_t *d_flags = ctx->d_stage + (size_t)c * 4;
         CK(cudaMemcpyAsync(d_slots, slots + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d_flags, flags + done, (size_t)c, cudaMemcpyHostToDevice, s));
-        k_update_flags<<<std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8), 256, 0, s>>>(ctx->d_meta, d_slots, d_flags, c);
+        k_update_flags<<<std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8), 256, 0, s>>>(ctx->d_tiles, d_slots, d_flags, c);
         CK_LAUNCH();
         done += c;
     }
@@ -586,6 +574,8 @@ int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t en
     for (uint64_t i = 0; i < n_rec; ++i)
         astre_host::extract_view(clip16 + 16 * i, phase_mask[i % views_per_world] & 15u, &recs[i]);
     if (n_rec) CK(cudaMemcpy(ctx->d_views, recs.data(), n_rec * sizeof(ViewDev), cudaMemcpyHostToDevice));
+    std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
+    if (n_worlds == 1 && views_per_world) std::memcpy(ctx->h_viewset.v, recs.data(), views_per_world * sizeof(ViewDev));
     ctx->n_worlds = n_worlds;
     ctx->entities_per_world = n_worlds > 1 ? entities_per_world : 0;
     ctx->views_per_world = views_per_world;
@@ -622,24 +612,34 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     CK_LAUNCH();
 
     const FrameParams P = params_of(ctx, cull);
-    const int stage_bytes = kWarpsPerBlock * kStageF4PerWarp * (int)sizeof(float4);
-    const uint32_t max_grid = (uint32_t)(ctx->sm_count * ctx->cull_blocks_per_sm);
     CK(cudaEventRecord(ctx->ev_cull0, s));
     if (n) {
+        const bool worlds = ctx->n_worlds > 1;
+        const uint32_t fused_grid = (uint32_t)(ctx->sm_count * ctx->fused_blocks_per_sm);
+        // one launch over the slot range [lo, hi); hier = world[parent] * local
+        auto launch_range = [&](uint32_t lo, uint32_t hi, bool hier) {
+            const uint32_t base0 = lo & ~(uint32_t)(kWarpTile - 1);
+            const uint32_t tiles = ceil_div((uint64_t)hi - base0, kBlockTile);
+            const uint32_t g = std::min(tiles, fused_grid);
+            if (!cull) {
+                if (hier) k_frame_fused<true, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                else k_frame_fused<false, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+            } else if (hier) {
+                if (worlds) k_frame_fused<true, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                else k_frame_fused<true, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+            } else {
+                if (worlds) k_frame_fused<false, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                else k_frame_fused<false, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+            }
+        };
         if (!ctx->has_parents) {
-            const uint32_t tiles = ceil_div(n, kBlockTile);
-            k_transform_cull<false><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, 0u, n);
+            launch_range(0u, n, false);
             CK_LAUNCH();
         } else {
             for (size_t l = 0; l < ctx->levels.size(); ++l) {
                 const Level &L = ctx->levels[l];
                 if (L.contiguous) {
-                    const uint32_t base0 = L.first & ~(uint32_t)(kWarpTile - 1);
-                    const uint32_t tiles = ceil_div((uint64_t)L.first + L.count - base0, kBlockTile);
-                    if (l == 0)
-                        k_transform_cull<false><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, L.first, L.first + L.count);
-                    else
-                        k_transform_cull<true><<<std::min(tiles, max_grid), kBlockThreads, stage_bytes, s>>>(P, L.first, L.first + L.count);
+                    launch_range(L.first, L.first + L.count, l != 0);
                 } else {
                     const uint32_t grid = std::min<uint32_t>(ceil_div(L.count, kBlockThreads), (uint32_t)ctx->sm_count * 8);
                     k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(P, ctx->d_level_slots + L.list_offset, L.count);
@@ -656,7 +656,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             float *b = ctx->d_basis;
             const size_t stride = (size_t)ctx->cap_entities * 3;
             k_basis<<<std::min<uint32_t>(ceil_div(n, 256), ctx->sm_count * 8), 256, 0, s>>>(
-                ctx->plane(3), ctx->plane(4), ctx->plane(5), ctx->plane(6), b, b + stride, b + 2 * stride, n);
+                ctx->d_tiles, b, b + stride, b + 2 * stride, n);
             CK_LAUNCH();
         }
     }
@@ -726,8 +726,8 @@ int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream)
     if (!ctx) return ASTRE_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (!ctx->d_prev) CK(cudaMalloc(&ctx->d_prev, (size_t)ctx->cap_entities * 10 * sizeof(float)));
-    CK(cudaMemcpyAsync(ctx->d_prev, ctx->d_planes, (size_t)ctx->cap_entities * 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (!ctx->d_prev) CK(cudaMalloc(&ctx->d_prev, ctx->tile_words() * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->d_prev, ctx->d_tiles, ctx->tile_words() * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return ASTRE_OK;
 }
 

@@ -51,12 +51,17 @@ __device__ __forceinline__ void mat4_mul(const float (&a)[16], const float (&b)[
 }
 
 // The op-for-op chain translate(I,p) * toMat4(q) * scale(I,s) of
-// transform_system.cpp:51-57.  Used only when the short form below cannot
-// guarantee identical bits (a -0 product or a non-finite operand).
-__device__ __noinline__ void trs_chain(float px, float py, float pz, const float (&rot)[9],
-                                       float sx, float sy, float sz, float (&m)[16])
+// transform_system.cpp:51-57, written to `dst` (four float4 columns in shared
+// memory).  Used only when the short form below cannot guarantee identical
+// bits (a -0 involved, or a non-finite operand).  Out of line and fed by value
+// so that the caller keeps its matrix in registers: the arrays here live on
+// this function's own stack.
+__device__ __noinline__ void trs_chain_store(float px, float py, float pz, float qx, float qy, float qz, float qw,
+                                             float sx, float sy, float sz, float4 *dst)
 {
-    float T[16], R[16], S[16], TR[16];
+    float rot[9];
+    quat_to_rot(qx, qy, qz, qw, rot);
+    float T[16], R[16], S[16], TR[16], m[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { T[i] = 0.0f; R[i] = 0.0f; S[i] = 0.0f; }
     T[0] = T[5] = T[10] = 1.0f;
@@ -82,6 +87,10 @@ __device__ __noinline__ void trs_chain(float px, float py, float pz, const float
     S[15] = 1.0f;
     mat4_mul(T, R, TR);
     mat4_mul(TR, S, m);
+    dst[0] = make_float4(m[0], m[1], m[2], m[3]);
+    dst[1] = make_float4(m[4], m[5], m[6], m[7]);
+    dst[2] = make_float4(m[8], m[9], m[10], m[11]);
+    dst[3] = make_float4(m[12], m[13], m[14], m[15]);
 }
 
 // World matrix of one root entity.  For finite inputs every element of
@@ -90,10 +99,11 @@ __device__ __noinline__ void trs_chain(float px, float py, float pz, const float
 //   M[c][r] = R[c][r]*s_c          (c,r < 3; exact unless a -0 is involved)
 //   M[c][3] = copysign(0, s_c)     M[3][r] = p_r + 0 (-0 -> +0)     M[3][3] = 1
 // A -0 rotation element or product, or Inf/NaN anywhere, takes the full chain,
-// where the other zero terms decide the sign.
+// where the other zero terms decide the sign.  `scratch` is a 64-byte shared
+// memory slot private to the calling thread (the chain's result passes through it).
 __device__ __forceinline__ void trs_matrix(float px, float py, float pz,
                                            float qx, float qy, float qz, float qw,
-                                           float sx, float sy, float sz, float (&m)[16])
+                                           float sx, float sy, float sz, float (&m)[16], float4 *scratch)
 {
     float rot[9];
     quat_to_rot(qx, qy, qz, qw, rot);
@@ -119,7 +129,14 @@ __device__ __forceinline__ void trs_matrix(float px, float py, float pz,
     lo = min(lo, min(min(__float_as_int(rot[0]), __float_as_int(rot[1])), __float_as_int(rot[2])));
     lo = min(lo, min(min(__float_as_int(rot[3]), __float_as_int(rot[4])), __float_as_int(rot[5])));
     lo = min(lo, min(min(__float_as_int(rot[6]), __float_as_int(rot[7])), __float_as_int(rot[8])));
-    if (!(chk == 0.0f) || lo == (int)0x80000000) trs_chain(px, py, pz, rot, sx, sy, sz, m);
+    if (!(chk == 0.0f) || lo == (int)0x80000000) {
+        trs_chain_store(px, py, pz, qx, qy, qz, qw, sx, sy, sz, scratch);
+        const float4 c0 = scratch[0], c1 = scratch[1], c2 = scratch[2], c3 = scratch[3];
+        m[0] = c0.x; m[1] = c0.y; m[2] = c0.z; m[3] = c0.w;
+        m[4] = c1.x; m[5] = c1.y; m[6] = c1.z; m[7] = c1.w;
+        m[8] = c2.x; m[9] = c2.y; m[10] = c2.z; m[11] = c2.w;
+        m[12] = c3.x; m[13] = c3.y; m[14] = c3.z; m[15] = c3.w;
+    }
 }
 
 // forward/up/right of transform_system.cpp:59-61: normalize(q*(0,0,-1)),

@@ -89,7 +89,8 @@ struct ViewHost {
     float depth[4];
     float depth_scale;
     uint32_t phase_mask;
-    uint32_t pad[2];
+    uint32_t sym;     // bit i: planes 2i, 2i+1 share bit-identical |n| and length
+    uint32_t pad;
 };
 
 // Frustum planes of clip = P*V for the GL clip volume -w <= x,y,z <= w
@@ -119,7 +120,10 @@ inline void extract_view(const float *clip, uint32_t phase_mask, ViewHost *v)
     const float scale = 16384.0f / range;
     v->depth_scale = (range > 0.0f && scale < INFINITY) ? scale : 0.0f;
     v->phase_mask = phase_mask;
-    v->pad[0] = v->pad[1] = 0;
+    v->sym = 0;
+    for (int i = 0; i < 3; ++i)
+        if (std::memcmp(v->aplane[2 * i], v->aplane[2 * i + 1], 4 * sizeof(float)) == 0) v->sym |= 1u << i;
+    v->pad = 0;
 }
 
 }  // namespace astre_host

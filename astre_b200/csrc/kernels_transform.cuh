@@ -1,25 +1,24 @@
-// K1+K2: fused transform + frustum cull + stream compaction + key emission.
+// Shared definitions of the transform + visibility kernels: the device mirror
+// layout, the culling arithmetic (spec: SURVEY.md Appendix B) and the indexed
+// fallback kernel.  The main kernel is in kernels_fused.cuh.
 //
 // Replaces the per-entity loops of TransformSystem::run
 // (engine/modules/ECS/src/system/transform_system.cpp:21-67), VisualSystem::run
 // (engine/modules/ECS/src/system/visual_system.cpp:20-58) and the per-pass
 // filters of deferredShadingStage (engine/modules/Pipeline/src/deferred_shading.cpp:115-121,151-156).
 //
-// Data layout in HBM (the device mirror of the component storages):
-//   px,py,pz,qx,qy,qz,qw,sx,sy,sz  one float plane per component, index = slot
-//   meta                           u32 per slot: mesh[10:0] | shader[18:11] | flags[23:19]
-//   parent                         u32 per slot (ASTRE_NO_PARENT = root)
-//   world                          float4[slot*4 + column], GLM column-major mat4
-// Every plane is padded to a multiple of kBlockTile entities so that the
-// 128-bit loads of a partial tile stay inside the allocation.
-//
-// Work decomposition: a block tile is 1024 consecutive slots, a warp tile 128,
-// and lane L owns slots 4L..4L+3 of its warp tile, so every component is read
-// with one coalesced 128-bit load per lane (512 B per warp instruction).  The
-// four matrices a lane produces (256 B) are staged in shared memory with a
-// 16-byte pad after every 256 B, which makes both the lane-strided STS.128
-// and the drain's linear LDS.128 conflict-free; the drain then writes the warp
-// tile's 8 KB with fully coalesced 128-bit stores.
+// Data layout in HBM -- the mirror of the component storages
+// (engine/modules/ECS/include/ecs/component_manager.hpp:34-90), tile-major SoA:
+//   tiles   one 6144-byte record per 128 consecutive slots; the record holds twelve
+//           128-element planes: px py pz | qx qy qz qw | sx sy sz | meta | parent
+//           (meta = mesh[10:0] | shader[18:11] | flags[23:19]; parent = slot or
+//           ASTRE_NO_PARENT).  A warp tile's whole input is therefore ONE
+//           contiguous 5632-byte (flat) or 6144-byte (hierarchy) block: one TMA
+//           bulk copy, one DRAM page run, and every plane inside it is read with
+//           conflict-free 128-bit shared loads.
+//   world   float4[slot*4 + column], GLM column-major mat4 (the reference's
+//           transform_matrix layout, engine/modules/Math/src/math.cpp:70-93)
+// The tile array is padded by one block tile beyond max_entities.
 //
 // Algorithmic HBM bytes per entity: 40 (TRS) + 4 (meta) + 64 (world) = 108,
 // + 4 + 64 for a non-root entity (parent index + parent matrix), + 8 per key.
@@ -33,8 +32,17 @@ constexpr int kWarpsPerBlock = kBlockThreads / 32;
 constexpr int kPerLane = 4;
 constexpr int kWarpTile = 32 * kPerLane;               // 128 entities
 constexpr int kBlockTile = kWarpsPerBlock * kWarpTile; // 1024 entities
-constexpr int kStageF4PerWarp = kWarpTile * 4 + kWarpTile / 4;  // 512 + 32 pad slots
 constexpr uint32_t kNoParent = 0xFFFFFFFFu;
+
+// tile record
+constexpr int kTilePlanes = 12;
+constexpr int kTileFloats = kTilePlanes * kWarpTile;   // 1536 words = 6144 B
+enum Plane { PX = 0, PY, PZ, QX, QY, QZ, QW, SX, SY, SZ, META, PARENT };
+
+__host__ __device__ __forceinline__ size_t tile_index(uint32_t slot, int plane)
+{
+    return (size_t)(slot >> 7) * kTileFloats + (size_t)plane * kWarpTile + (slot & 127u);
+}
 
 // One view on the device (224 B, 16-byte aligned).
 struct ViewDev {
@@ -43,11 +51,12 @@ struct ViewDev {
     float4 depth;      // normalised near plane
     float depth_scale;
     uint32_t phase_mask;
-    uint32_t pad[2];
+    uint32_t sym;      // bit i: planes 2i and 2i+1 have bit-identical (|n|, len) (orthographic pairs)
+    uint32_t pad;
 };
 static_assert(sizeof(ViewDev) == 224, "ViewDev layout");
 
-struct BoundsDev {   // 32 B
+struct BoundsDev {   // 32 B; extents and radius are >= 0 (checked by astre_gpu_set_mesh_bounds)
     float cx, cy, cz, ex;
     float ey, ez, r;
     uint32_t reserved;
@@ -60,9 +69,7 @@ struct FrameControl {            // one per context, zeroed at the start of a fr
 };
 
 struct FrameParams {
-    const float *px, *py, *pz, *qx, *qy, *qz, *qw, *sx, *sy, *sz;
-    const uint32_t *meta;
-    const uint32_t *parent;
+    const float *tiles;            // tile-major mirror
     float4 *world;
     const BoundsDev *bounds;
     const ViewDev *views;          // [n_worlds][views_per_world]
@@ -86,13 +93,10 @@ __device__ __forceinline__ uint32_t u4get(const uint4 &v, int k)
     return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
 }
 
-__device__ __forceinline__ float4 ld_stream(const float *p)
-{
-    return __ldcs(reinterpret_cast<const float4 *>(p));
-}
-
-// World-space bounds (spec; mirrored by the CPU checker).
-struct WorldBounds { float cx, cy, cz, ex, ey, ez, r; };
+// World-space bounds (spec; the CPU checker restates it).
+// rho is NOT part of the spec: an upper bound (with margin) on the support
+// radius per unit plane length, used only to skip work whose outcome is certain.
+struct WorldBounds { float cx, cy, cz, ex, ey, ez, r, rho; };
 
 __device__ __forceinline__ WorldBounds world_bounds(const float (&m)[16], const BoundsDev &b)
 {
@@ -107,15 +111,20 @@ __device__ __forceinline__ WorldBounds world_bounds(const float (&m)[16], const 
     const float l1 = ffma(m[4], m[4], ffma(m[5], m[5], fmul(m[6], m[6])));
     const float l2 = ffma(m[8], m[8], ffma(m[9], m[9], fmul(m[10], m[10])));
     w.r = fmul(b.r, __fsqrt_rn(fmaxf(fmaxf(l0, l1), l2)));
+    // |n|.e' + r'*len <= len*(ex+ey+ez+r') because every |n_i| <= len; 1.0001 and
+    // 1e-20 swallow the (< 2^-20 relative, few-ulp-of-denormal absolute) rounding
+    // of both sides.
+    w.rho = ffma(fadd(fadd(fadd(w.ex, w.ey), w.ez), w.r), 1.0001f, 1e-20f);
     return w;
 }
 
-// 1 if the plane rejects the bounds: dist + rad < 0 (false on NaN).
-__device__ __forceinline__ bool plane_rejects(const WorldBounds &w, const float4 &pl, const float4 &ap)
+__device__ __forceinline__ float plane_dist(const WorldBounds &w, const float4 &pl)
 {
-    const float dist = ffma(pl.x, w.cx, ffma(pl.y, w.cy, ffma(pl.z, w.cz, pl.w)));
-    const float rad = ffma(ap.x, w.ex, ffma(ap.y, w.ey, ffma(ap.z, w.ez, fmul(w.r, ap.w))));
-    return fadd(dist, rad) < 0.0f;
+    return ffma(pl.x, w.cx, ffma(pl.y, w.cy, ffma(pl.z, w.cz, pl.w)));
+}
+__device__ __forceinline__ float plane_rad(const WorldBounds &w, const float4 &ap)
+{
+    return ffma(ap.x, w.ex, ffma(ap.y, w.ey, ffma(ap.z, w.ez, fmul(w.r, ap.w))));
 }
 
 __device__ __forceinline__ uint32_t depth14(const WorldBounds &w, const float4 &dp, float scale)
@@ -150,41 +159,82 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// Tests the (up to) kPerLane entities of one lane against the views of their
-// world.  vis[k] gets bit v set when entity k passes view v.  The plane loop
-// leaves early when no lane of the warp has a survivor (warp-uniform branch).
-template <int K>
-__device__ __forceinline__ void cull_views(const FrameParams &P, const ViewDev *vw,
-                                           const WorldBounds (&wb)[K], const uint32_t (&phases)[K],
-                                           uint32_t (&vis)[K])
+// View access: constant bank (one world; the records are a kernel parameter) or
+// global memory (batched worlds, one record set per world).
+constexpr int kMaxParamViews = 32;            // == ASTRE_MAX_VIEWS
+struct ViewSet { ViewDev v[kMaxParamViews]; };
+
+struct ConstViews {
+    const ViewSet &vs;
+    __device__ __forceinline__ float4 plane(uint32_t v, int p) const { return vs.v[v].plane[p]; }
+    __device__ __forceinline__ float4 aplane(uint32_t v, int p) const { return vs.v[v].aplane[p]; }
+    __device__ __forceinline__ float4 depth(uint32_t v) const { return vs.v[v].depth; }
+    __device__ __forceinline__ float depth_scale(uint32_t v) const { return vs.v[v].depth_scale; }
+    __device__ __forceinline__ uint32_t mask(uint32_t v) const { return vs.v[v].phase_mask; }
+    __device__ __forceinline__ uint32_t sym(uint32_t v) const { return vs.v[v].sym; }
+};
+struct GlobalViews {
+    const ViewDev *vw;
+    __device__ __forceinline__ float4 plane(uint32_t v, int p) const { return __ldg(&vw[v].plane[p]); }
+    __device__ __forceinline__ float4 aplane(uint32_t v, int p) const { return __ldg(&vw[v].aplane[p]); }
+    __device__ __forceinline__ float4 depth(uint32_t v) const { return __ldg(&vw[v].depth); }
+    __device__ __forceinline__ float depth_scale(uint32_t v) const { return __ldg(&vw[v].depth_scale); }
+    __device__ __forceinline__ uint32_t mask(uint32_t v) const { return __ldg(&vw[v].phase_mask); }
+    __device__ __forceinline__ uint32_t sym(uint32_t v) const { return __ldg(&vw[v].sym); }
+};
+
+// Tests the K entities of one lane against the F views of their world; vis[k]
+// gets bit v when entity k passes view v.  Specification per plane: reject iff
+// dist + rad < 0.  Evaluation: dist first; dist >= 0 cannot be rejected (rad >= 0),
+// dist + rho*len < 0 is certainly rejected (rho*len >= rad), and only when some
+// lane of the warp falls between the two is rad computed (exactly as specified).
+// The plane loop leaves as soon as no lane of the warp has a survivor.
+template <int K, class Views>
+__device__ __forceinline__ void cull_views(const Views &V, const uint32_t F, const WorldBounds (&wb)[K],
+                                           const uint32_t (&phases)[K], uint32_t (&vis)[K])
 {
-    const uint32_t F = P.views_per_world;
     for (uint32_t v = 0; v < F; ++v) {
-        const uint32_t mask = __ldg(&vw[v].phase_mask);
-        uint32_t alive = 0;
+        const uint32_t mask = V.mask(v);
+        bool alive[K], any = false;
 #pragma unroll
-        for (int k = 0; k < K; ++k) alive |= ((phases[k] & mask) ? 1u : 0u) << k;
-        if (!__any_sync(0xffffffffu, alive != 0)) continue;
-#pragma unroll 1
+        for (int k = 0; k < K; ++k) { alive[k] = (phases[k] & mask) != 0; any |= alive[k]; }
+        if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
         for (int p = 0; p < 6; ++p) {
-            const float4 pl = __ldg(&vw[v].plane[p]);
-            const float4 ap = __ldg(&vw[v].aplane[p]);
+            const float4 pl = V.plane(v, p);
+            const float len = V.aplane(v, p).w;
+            float d[K];
+            bool band = false;
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (plane_rejects(wb[k], pl, ap)) alive &= ~(1u << k);
-            if (!__any_sync(0xffffffffu, alive != 0)) break;
+            for (int k = 0; k < K; ++k) {
+                d[k] = plane_dist(wb[k], pl);
+                const bool out = ffma(wb[k].rho, len, d[k]) < 0.0f;     // certain reject
+                alive[k] = alive[k] && !out;
+                band |= alive[k] && !(d[k] >= 0.0f);                    // undecided (includes NaN)
+            }
+            if (__any_sync(0xffffffffu, band)) {
+                const float4 ap = V.aplane(v, p);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    alive[k] = alive[k] && !(fadd(d[k], plane_rad(wb[k], ap)) < 0.0f);
+            }
+            any = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) any |= alive[k];
+            if (p < 5 && !__any_sync(0xffffffffu, any)) break;
         }
 #pragma unroll
-        for (int k = 0; k < K; ++k) vis[k] |= ((alive >> k) & 1u) << v;
+        for (int k = 0; k < K; ++k) vis[k] |= (alive[k] ? 1u : 0u) << v;
     }
 }
 
-// Writes the keys of one lane starting at `pos` (a position in the key buffer).
-template <int K>
-__device__ __forceinline__ void emit_keys(const FrameParams &P, const ViewDev *vw, uint32_t world,
+// Writes the keys of one lane starting at `pos`; with s_counts != nullptr also
+// bumps the per-view shared counters (one world, sparse case).
+template <int K, class Views>
+__device__ __forceinline__ void emit_keys(const FrameParams &P, const Views &V, uint32_t world,
                                           const WorldBounds (&wb)[K], const uint32_t (&vis)[K],
                                           const uint32_t (&meta)[K], const uint32_t (&local)[K],
-                                          unsigned long long pos)
+                                          unsigned long long pos, uint32_t *s_counts)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -192,19 +242,18 @@ __device__ __forceinline__ void emit_keys(const FrameParams &P, const ViewDev *v
         while (m) {
             const uint32_t v = __ffs(m) - 1;
             m &= m - 1;
-            const float4 dp = __ldg(&vw[v].depth);
-            const float sc = __ldg(&vw[v].depth_scale);
-            const unsigned long long key = make_key(P.world_bits, world, v, (meta[k] >> 11) & 255u,
-                                                    meta[k] & 2047u, depth14(wb[k], dp, sc), local[k]);
+            const unsigned long long key = make_key(P.world_bits, world, v, (meta[k] >> 11) & 255u, meta[k] & 2047u,
+                                                    depth14(wb[k], V.depth(v), V.depth_scale(v)), local[k]);
             if (pos < P.key_cap) P.keys[pos] = key;
             else P.ctl->overflow = 1u;
             ++pos;
+            if (s_counts) atomicAdd(&s_counts[v], 1u);
         }
     }
 }
 
-// Per-(world,view) counts.  One world: warp-reduce then one shared atomic per
-// view per warp; many worlds: one global atomic per lane that has hits.
+// Per-(world,view) counts, dense case.  One world: warp-reduce then one shared
+// atomic per view per warp; many worlds: one global atomic per lane with hits.
 template <int K>
 __device__ __forceinline__ void add_counts(const FrameParams &P, uint32_t world, const uint32_t (&vis)[K],
                                            uint32_t *s_counts, int lane)
@@ -229,148 +278,26 @@ __device__ __forceinline__ void add_counts(const FrameParams &P, uint32_t world,
 }
 
 // ---------------------------------------------------------------------------
-// Range kernel: slots [first, end) in slot order.  HIER = the range is one
-// hierarchy level below the roots: world = world[parent] * local.
-// Grid: persistent, blocks stride over block tiles starting at first & ~127.
-// ---------------------------------------------------------------------------
-template <bool HIER>
-__global__ void __launch_bounds__(kBlockThreads, 2)
-k_transform_cull(const FrameParams P, const uint32_t first, const uint32_t end)
-{
-    extern __shared__ float4 s_stage[];                 // kWarpsPerBlock * kStageF4PerWarp
-    __shared__ uint32_t s_warp_cnt[kWarpsPerBlock];
-    __shared__ unsigned long long s_block_base;
-    __shared__ uint32_t s_counts[32];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *stage = s_stage + warp * kStageF4PerWarp;
-    const bool cull = P.views_per_world != 0;
-    if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
-    __syncthreads();
-
-    const uint32_t base0 = first & ~(uint32_t)(kWarpTile - 1);
-    const uint32_t n_tiles = (end - base0 + kBlockTile - 1) / kBlockTile;
-
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t wbase = base0 + tile * kBlockTile + warp * kWarpTile;
-        const uint32_t s0 = wbase + lane * kPerLane;
-
-        const float4 PX = ld_stream(P.px + s0), PY = ld_stream(P.py + s0), PZ = ld_stream(P.pz + s0);
-        const float4 QX = ld_stream(P.qx + s0), QY = ld_stream(P.qy + s0), QZ = ld_stream(P.qz + s0);
-        const float4 QW = ld_stream(P.qw + s0);
-        const float4 SX = ld_stream(P.sx + s0), SY = ld_stream(P.sy + s0), SZ = ld_stream(P.sz + s0);
-        const uint4 MT = __ldcs(reinterpret_cast<const uint4 *>(P.meta + s0));
-        uint4 PAR = make_uint4(kNoParent, kNoParent, kNoParent, kNoParent);
-        if (HIER) PAR = __ldcs(reinterpret_cast<const uint4 *>(P.parent + s0));
-
-        WorldBounds wb[kPerLane];
-        uint32_t phases[kPerLane], vis[kPerLane], meta[kPerLane], local[kPerLane];
-        const uint32_t world = (P.n_worlds > 1) ? min(s0 / P.entities_per_world, P.n_worlds - 1u) : 0u;
-
-#pragma unroll
-        for (int k = 0; k < kPerLane; ++k) {
-            const uint32_t slot = s0 + k;
-            const bool active = slot >= first && slot < end;
-            float m[16];
-            trs_matrix(f4get(PX, k), f4get(PY, k), f4get(PZ, k),
-                       f4get(QX, k), f4get(QY, k), f4get(QZ, k), f4get(QW, k),
-                       f4get(SX, k), f4get(SY, k), f4get(SZ, k), m);
-            if (HIER) {
-                const uint32_t par = u4get(PAR, k);
-                if (active && par != kNoParent) {
-                    const float4 *pw = P.world + (size_t)par * 4;
-                    const float4 a0 = pw[0], a1 = pw[1], a2 = pw[2], a3 = pw[3];
-                    const float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
-                                         a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-                    float w[16];
-                    mat4_mul(a, m, w);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) m[i] = w[i];
-                }
-            }
-            // stage: entity e = 4*lane+k of the warp tile, one pad slot per 4 entities
-            float4 *dst = stage + (lane * kPerLane + k) * 4 + lane;
-            dst[0] = make_float4(m[0], m[1], m[2], m[3]);
-            dst[1] = make_float4(m[4], m[5], m[6], m[7]);
-            dst[2] = make_float4(m[8], m[9], m[10], m[11]);
-            dst[3] = make_float4(m[12], m[13], m[14], m[15]);
-
-            meta[k] = u4get(MT, k);
-            vis[k] = 0;
-            local[k] = slot - world * P.entities_per_world;
-            const uint32_t flags = (meta[k] >> 19) & 31u;
-            const uint32_t mesh = meta[k] & 2047u;
-            const bool cand = cull && active && (flags & 1u) && mesh < P.n_meshes;
-            phases[k] = cand ? (flags >> 1) : 0u;
-            const BoundsDev b = P.bounds[cand ? mesh : 0u];
-            wb[k] = world_bounds(m, b);
-        }
-
-        if (cull) {
-            const ViewDev *vw = P.views + (size_t)world * P.views_per_world;
-            cull_views<kPerLane>(P, vw, wb, phases, vis);
-
-            // block-scan compaction: warp scan -> per-warp totals -> one reservation per block tile
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int k = 0; k < kPerLane; ++k) cnt += __popc(vis[k]);
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            if (lane == 31) s_warp_cnt[warp] = incl;
-            __syncthreads();
-            uint32_t block_total = 0, warp_off = 0;
-#pragma unroll
-            for (int w = 0; w < kWarpsPerBlock; ++w) {
-                const uint32_t c = s_warp_cnt[w];
-                if (w < warp) warp_off += c;
-                block_total += c;
-            }
-            if (threadIdx.x == 0 && block_total)
-                s_block_base = atomicAdd(&P.ctl->key_total, (unsigned long long)block_total);
-            __syncthreads();
-            if (block_total) {
-                if (__shfl_sync(0xffffffffu, incl, 31)) add_counts<kPerLane>(P, world, vis, s_counts, lane);
-                if (cnt) emit_keys<kPerLane>(P, vw, world, wb, vis, meta, local,
-                                             s_block_base + warp_off + (incl - cnt));
-            }
-        }
-
-        // drain the warp tile: 16 coalesced 128-bit stores per lane
-        __syncwarp();
-        float4 *out = P.world + (size_t)wbase * 4;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int j = i * 32 + lane;
-            const uint32_t slot = wbase + (j >> 2);
-            const float4 v = stage[j + (j >> 4)];
-            if (slot >= first && slot < end) {
-                if (HIER) out[j] = v; else __stcs(out + j, v);
-            }
-        }
-        __syncwarp();
-    }
-
-    __syncthreads();
-    if (cull && P.n_worlds == 1 && threadIdx.x < P.views_per_world && s_counts[threadIdx.x])
-        atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
-}
-
-// ---------------------------------------------------------------------------
-// Indexed kernel: one hierarchy level given as a slot list (slots of the level
-// are not contiguous).  One entity per thread, warp-aggregated compaction.
+// Indexed kernel: one hierarchy level given as a slot list (the slots of the
+// level are not a contiguous range).  One entity per thread, warp-aggregated
+// compaction.  Correct for any slot order; the range kernel is the fast path.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlockThreads)
 k_transform_cull_indexed(const FrameParams P, const uint32_t *__restrict__ slots, const uint32_t n)
 {
+    __shared__ float4 s_scratch[kBlockThreads * 4];
     const int lane = threadIdx.x & 31;
     const bool cull = P.views_per_world != 0;
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n;
         const uint32_t slot = active ? slots[i] : 0u;
+        const float *t = P.tiles + tile_index(slot, 0);
         float m[16];
-        trs_matrix(P.px[slot], P.py[slot], P.pz[slot], P.qx[slot], P.qy[slot], P.qz[slot], P.qw[slot],
-                   P.sx[slot], P.sy[slot], P.sz[slot], m);
-        const uint32_t par = P.parent ? P.parent[slot] : kNoParent;
+        trs_matrix(t[PX * kWarpTile], t[PY * kWarpTile], t[PZ * kWarpTile],
+                   t[QX * kWarpTile], t[QY * kWarpTile], t[QZ * kWarpTile], t[QW * kWarpTile],
+                   t[SX * kWarpTile], t[SY * kWarpTile], t[SZ * kWarpTile], m, s_scratch + threadIdx.x * 4);
+        const uint32_t par = __float_as_uint(t[PARENT * kWarpTile]);
         if (active && par != kNoParent) {
             const float4 *pw = P.world + (size_t)par * 4;
             const float4 a0 = pw[0], a1 = pw[1], a2 = pw[2], a3 = pw[3];
@@ -390,15 +317,15 @@ k_transform_cull_indexed(const FrameParams P, const uint32_t *__restrict__ slots
         }
         if (!cull) continue;
         const uint32_t world = (P.n_worlds > 1) ? slot / P.entities_per_world : 0u;
-        uint32_t meta[1] = { P.meta[slot] }, vis[1] = { 0 }, phases[1], local[1];
+        uint32_t meta[1] = { __float_as_uint(t[META * kWarpTile]) }, vis[1] = { 0 }, phases[1], local[1];
         local[0] = slot - world * P.entities_per_world;
         const uint32_t flags = (meta[0] >> 19) & 31u, mesh = meta[0] & 2047u;
         const bool cand = active && (flags & 1u) && mesh < P.n_meshes;
         phases[0] = cand ? (flags >> 1) : 0u;
         WorldBounds wb[1];
         wb[0] = world_bounds(m, P.bounds[cand ? mesh : 0u]);
-        const ViewDev *vw = P.views + (size_t)world * P.views_per_world;
-        cull_views<1>(P, vw, wb, phases, vis);
+        const GlobalViews V{ P.views + (size_t)world * P.views_per_world };
+        cull_views<1>(V, P.views_per_world, wb, phases, vis);
         const uint32_t cnt = __popc(vis[0]);
         const uint32_t incl = warp_incl_scan(cnt, lane);
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
@@ -408,7 +335,7 @@ k_transform_cull_indexed(const FrameParams P, const uint32_t *__restrict__ slots
             base = __shfl_sync(0xffffffffu, base, 0);
             for (uint32_t v = 0; v < P.views_per_world; ++v)
                 if ((vis[0] >> v) & 1u) atomicAdd(&P.counts[(size_t)world * P.views_per_world + v], 1u);
-            if (cnt) emit_keys<1>(P, vw, world, wb, vis, meta, local, base + (incl - cnt));
+            if (cnt) emit_keys<1>(P, V, world, wb, vis, meta, local, base + (incl - cnt), nullptr);
         }
     }
 }
