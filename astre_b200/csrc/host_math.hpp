@@ -82,7 +82,7 @@ inline void ortho(float l, float r, float b, float t, float zn, float zf, float 
     m[14] = -(zf + zn) / (zf - zn);
 }
 
-// Host image of the device view record (same 224-byte layout as astre::ViewDev).
+// Host image of the device view record (same 256-byte layout as astre::ViewDev).
 struct ViewHost {
     float plane[6][4];
     float aplane[6][4];
@@ -91,7 +91,58 @@ struct ViewHost {
     uint32_t phase_mask;
     uint32_t sym;     // bit i: planes 2i, 2i+1 share bit-identical |n| and length
     uint32_t pad;
+    float lo[4];      // world-space box around the view volume (xyz)
+    float hi[4];
 };
+
+// World-space box around the view volume (spec, SURVEY.md Appendix B extension):
+// the eight NDC corners through the adjugate of the clip matrix in double
+// precision, widened by 1e-4 of its size + 1e-6 and rounded outwards to float;
+// unbounded when the matrix is singular or a corner has w <= 0.
+inline void view_box(const float *clip, float *lo4, float *hi4)
+{
+    double m[16], a[16];
+    for (int i = 0; i < 16; ++i) m[i] = (double)clip[i];
+    a[0]  =  m[5]*m[10]*m[15] - m[5]*m[11]*m[14] - m[9]*m[6]*m[15] + m[9]*m[7]*m[14] + m[13]*m[6]*m[11] - m[13]*m[7]*m[10];
+    a[4]  = -m[4]*m[10]*m[15] + m[4]*m[11]*m[14] + m[8]*m[6]*m[15] - m[8]*m[7]*m[14] - m[12]*m[6]*m[11] + m[12]*m[7]*m[10];
+    a[8]  =  m[4]*m[9]*m[15]  - m[4]*m[11]*m[13] - m[8]*m[5]*m[15] + m[8]*m[7]*m[13] + m[12]*m[5]*m[11] - m[12]*m[7]*m[9];
+    a[12] = -m[4]*m[9]*m[14]  + m[4]*m[10]*m[13] + m[8]*m[5]*m[14] - m[8]*m[6]*m[13] - m[12]*m[5]*m[10] + m[12]*m[6]*m[9];
+    a[1]  = -m[1]*m[10]*m[15] + m[1]*m[11]*m[14] + m[9]*m[2]*m[15] - m[9]*m[3]*m[14] - m[13]*m[2]*m[11] + m[13]*m[3]*m[10];
+    a[5]  =  m[0]*m[10]*m[15] - m[0]*m[11]*m[14] - m[8]*m[2]*m[15] + m[8]*m[3]*m[14] + m[12]*m[2]*m[11] - m[12]*m[3]*m[10];
+    a[9]  = -m[0]*m[9]*m[15]  + m[0]*m[11]*m[13] + m[8]*m[1]*m[15] - m[8]*m[3]*m[13] - m[12]*m[1]*m[11] + m[12]*m[3]*m[9];
+    a[13] =  m[0]*m[9]*m[14]  - m[0]*m[10]*m[13] - m[8]*m[1]*m[14] + m[8]*m[2]*m[13] + m[12]*m[1]*m[10] - m[12]*m[2]*m[9];
+    a[2]  =  m[1]*m[6]*m[15]  - m[1]*m[7]*m[14]  - m[5]*m[2]*m[15] + m[5]*m[3]*m[14] + m[13]*m[2]*m[7]  - m[13]*m[3]*m[6];
+    a[6]  = -m[0]*m[6]*m[15]  + m[0]*m[7]*m[14]  + m[4]*m[2]*m[15] - m[4]*m[3]*m[14] - m[12]*m[2]*m[7]  + m[12]*m[3]*m[6];
+    a[10] =  m[0]*m[5]*m[15]  - m[0]*m[7]*m[13]  - m[4]*m[1]*m[15] + m[4]*m[3]*m[13] + m[12]*m[1]*m[7]  - m[12]*m[3]*m[5];
+    a[14] = -m[0]*m[5]*m[14]  + m[0]*m[6]*m[13]  + m[4]*m[1]*m[14] - m[4]*m[2]*m[13] - m[12]*m[1]*m[6]  + m[12]*m[2]*m[5];
+    a[3]  = -m[1]*m[6]*m[11]  + m[1]*m[7]*m[10]  + m[5]*m[2]*m[11] - m[5]*m[3]*m[10] - m[9]*m[2]*m[7]   + m[9]*m[3]*m[6];
+    a[7]  =  m[0]*m[6]*m[11]  - m[0]*m[7]*m[10]  - m[4]*m[2]*m[11] + m[4]*m[3]*m[10] + m[8]*m[2]*m[7]   - m[8]*m[3]*m[6];
+    a[11] = -m[0]*m[5]*m[11]  + m[0]*m[7]*m[9]   + m[4]*m[1]*m[11] - m[4]*m[3]*m[9]  - m[8]*m[1]*m[7]   + m[8]*m[3]*m[5];
+    a[15] =  m[0]*m[5]*m[10]  - m[0]*m[6]*m[9]   - m[4]*m[1]*m[10] + m[4]*m[2]*m[9]  + m[8]*m[1]*m[6]   - m[8]*m[2]*m[5];
+    const double det = m[0]*a[0] + m[1]*a[4] + m[2]*a[8] + m[3]*a[12];
+    bool ok = (det != 0.0) && std::isfinite(det);
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int c = 0; c < 8 && ok; ++c) {
+        const double x = (c & 1) ? 1.0 : -1.0, y = (c & 2) ? 1.0 : -1.0, z = (c & 4) ? 1.0 : -1.0;
+        const double w = (a[3]*x + a[7]*y + a[11]*z + a[15]) / det;
+        if (!(w > 0.0) || !std::isfinite(w)) { ok = false; break; }
+        const double p[3] = { (a[0]*x + a[4]*y + a[8]*z  + a[12]) / det / w,
+                              (a[1]*x + a[5]*y + a[9]*z  + a[13]) / det / w,
+                              (a[2]*x + a[6]*y + a[10]*z + a[14]) / det / w };
+        for (int i = 0; i < 3; ++i) {
+            if (!std::isfinite(p[i])) ok = false;
+            if (p[i] < lo[i]) lo[i] = p[i];
+            if (p[i] > hi[i]) hi[i] = p[i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!ok) { lo4[i] = -INFINITY; hi4[i] = INFINITY; continue; }
+        const double d = (hi[i] - lo[i]) * 1e-4 + 1e-6;
+        lo4[i] = std::nextafterf((float)(lo[i] - d), -INFINITY);
+        hi4[i] = std::nextafterf((float)(hi[i] + d), INFINITY);
+    }
+    lo4[3] = 0.0f; hi4[3] = 0.0f;
+}
 
 // Frustum planes of clip = P*V for the GL clip volume -w <= x,y,z <= w
 // (engine/resources/shaders/glsl/deferred_shader/vertex.glsl:17-22 fixes the
@@ -124,6 +175,7 @@ inline void extract_view(const float *clip, uint32_t phase_mask, ViewHost *v)
     for (int i = 0; i < 3; ++i)
         if (std::memcmp(v->aplane[2 * i], v->aplane[2 * i + 1], 4 * sizeof(float)) == 0) v->sym |= 1u << i;
     v->pad = 0;
+    view_box(clip, v->lo, v->hi);
 }
 
 }  // namespace astre_host

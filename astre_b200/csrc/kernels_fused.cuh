@@ -3,7 +3,8 @@
 //
 // Work decomposition: persistent grid (2 CTAs per SM), a block tile is 1024
 // consecutive slots, a warp tile 128, and lane L owns slots 4L..4L+3 of its warp
-// tile.  Per warp tile:
+// tile.  Warps are independent: there is no block-wide barrier inside the loop.
+// Per warp tile:
 //
 //  * input: ONE cp.async.bulk (TMA, SASS UBLKCP) of the tile record (5632 or
 //    6144 B, kernels_transform.cuh) into the warp's shared buffer, completion on
@@ -14,11 +15,16 @@
 //  * output: matrices are staged two entities per lane at a time (lane stride of
 //    9 float4: conflict-free STS.128 / LDS.128) and drained with full-line 128-bit
 //    streaming stores;
-//  * cull: views come from the constant bank (kernel parameter) for one world;
-//    certain-outcome planes cost 4 FFMA + 2 compares per entity, the exact
-//    support radius is only evaluated when a lane is undecided;
-//  * compaction: warp ballot/scan -> block scan over 8 warp totals -> one global
-//    reservation per block tile -> keys written at base + warp + lane offset.
+//  * cull, step 1 (all entities x all views): box-vs-box, six compares against
+//    constant-bank operands per pair.  What survives is rare and scattered over
+//    the lanes, so
+//  * cull, step 2 runs on COMPACTED work: survivors are queued as (entity, view)
+//    tasks (warp ballot + prefix popc), the entity bounds wait in the now-idle
+//    staging buffer, and every 32 tasks one lane-per-task round does the six
+//    exact plane tests.  A view that keeps a large part of the tile (>= 40 of
+//    128) skips the queue and is tested four entities per lane instead;
+//  * compaction: keys are appended to a per-warp shared buffer (ballot + prefix
+//    popc) and flushed with one global reservation and coalesced 8-byte stores.
 #pragma once
 #include "kernels_transform.cuh"
 
@@ -26,10 +32,14 @@ namespace astre {
 
 constexpr int kInBytesFlat = 11 * kWarpTile * 4;           // 5632: planes px..meta
 constexpr int kInBytesHier = 12 * kWarpTile * 4;           // 6144: + parent
-constexpr int kHalfStageF4 = 32 * 9;                       // two entities per lane + one pad slot
-constexpr int kWarpSmemBytes = kInBytesHier + kHalfStageF4 * 16;   // 10752
-constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;   // 86016
-constexpr uint32_t kSmemMeshes = 256;   // bounds tables up to this size are served from shared memory
+constexpr int kStageBytes = 32 * 9 * 16;                   // 4608: half-tile staging, later 9 words x 128 entities
+constexpr int kKeyCap = 160;                               // per-warp key buffer (>= 128 + slack)
+constexpr int kQueueCap = 80;                              // per-warp task queue (< 32 + kDenseMin entries live)
+constexpr int kDenseMin = 40;                              // survivors per view and warp tile that take the dense path
+constexpr int kWarpSmemBytes = kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2;   // 12192
+constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;                           // 97536
+constexpr uint32_t kSmemMeshes = 64;    // bounds tables up to this size are served from shared memory
+constexpr uint32_t kSmemViews = 16;     // views up to this index can take the task path
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,6 +73,43 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 struct LaneInputs {
     float4 px, py, pz, qx, qy, qz, qw, sx, sy, sz;
     uint4 meta, parent;
+};
+
+// Per-warp output side: the key buffer and where it flushes to.
+struct KeySink {
+    unsigned long long *kbuf;     // shared, kKeyCap entries
+    uint32_t fill;                // warp-uniform
+    const FrameParams *P;
+    int lane;
+
+    __device__ __forceinline__ void flush()
+    {
+        __syncwarp();
+        if (fill) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P->ctl->key_total, (unsigned long long)fill);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (uint32_t i = lane; i < fill; i += 32) {
+                const unsigned long long pos = base + i;
+                if (pos < P->key_cap) P->keys[pos] = kbuf[i];
+                else P->ctl->overflow = 1u;
+            }
+        }
+        __syncwarp();
+        fill = 0;
+    }
+    // warp-collective: every lane calls it; lanes with `on` contribute `key`
+    __device__ __forceinline__ uint32_t append(bool on, unsigned long long key)
+    {
+        const uint32_t m = __ballot_sync(0xffffffffu, on);
+        const uint32_t c = __popc(m);
+        if (c) {
+            if (fill + c > (uint32_t)kKeyCap) flush();
+            if (on) kbuf[fill + __popc(m & ((1u << lane) - 1u))] = key;
+            fill += c;
+        }
+        return c;
+    }
 };
 
 // Transform + stage + drain of one warp tile (and the world-space bounds when
@@ -132,30 +179,48 @@ __device__ __forceinline__ void transform_tile(const FrameParams &P, const LaneI
     }
 }
 
+// Entity bounds parked in the staging buffer: word w of entity (lane L, k) at sb[w*128 + k*32 + L].
+__device__ __forceinline__ WorldBounds load_bounds(const float *sb, int idx)
+{
+    WorldBounds w;
+    w.cx = sb[0 * 128 + idx]; w.cy = sb[1 * 128 + idx]; w.cz = sb[2 * 128 + idx];
+    w.ex = sb[3 * 128 + idx]; w.ey = sb[4 * 128 + idx]; w.ez = sb[5 * 128 + idx];
+    w.r = sb[6 * 128 + idx];
+    return w;
+}
+
 template <bool HIER, bool WORLDS, bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uint32_t first, const uint32_t end)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(16) BoundsDev s_bounds[CULL ? kSmemMeshes : 1];
+    __shared__ __align__(16) ViewDev s_views[(CULL && !WORLDS) ? kSmemViews : 1];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
-    __shared__ uint32_t s_warp_cnt[kWarpsPerBlock];
-    __shared__ unsigned long long s_block_base;
     __shared__ uint32_t s_counts[32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *s_in = s_dyn + warp * kWarpSmemBytes;
     float4 *stage = reinterpret_cast<float4 *>(s_in + kInBytesHier);
+    float *sb = reinterpret_cast<float *>(stage);
+    unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(s_in + kInBytesHier + kStageBytes);
+    unsigned short *queue = reinterpret_cast<unsigned short *>(s_in + kInBytesHier + kStageBytes + kKeyCap * 8);
     const uint32_t bar = smem_u32(&s_bar[warp]);
     const uint32_t s_in_addr = smem_u32(s_in);
     const uint32_t F = P.views_per_world;
     const bool small_table = P.n_meshes <= kSmemMeshes;
     constexpr uint32_t kInBytes = HIER ? kInBytesHier : kInBytesFlat;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
     if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
     if (CULL && small_table) {
         for (uint32_t i = threadIdx.x; i < P.n_meshes * 2; i += kBlockThreads)   // 32-byte records, two float4 each
             reinterpret_cast<float4 *>(s_bounds)[i] = __ldg(reinterpret_cast<const float4 *>(P.bounds) + i);
+    }
+    if (CULL && !WORLDS) {
+        const uint32_t nv = F < kSmemViews ? F : kSmemViews;
+        for (uint32_t i = threadIdx.x; i < nv * 16; i += kBlockThreads)          // 256-byte records, 16 float4 each
+            reinterpret_cast<float4 *>(s_views)[i] = reinterpret_cast<const float4 *>(VS.v)[i];
     }
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -174,6 +239,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uin
         bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
     };
 
+    KeySink sink{ kbuf, 0u, &P, lane };
     uint32_t parity = 0;
     if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x);
 
@@ -201,52 +267,119 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uin
         }
 
         WorldBounds wb[kPerLane];
-        uint32_t phases[kPerLane], vis[kPerLane], meta[kPerLane], local[kPerLane];
+        uint32_t phases[kPerLane], meta[kPerLane], local[kPerLane];
         const uint32_t world = WORLDS ? min((wbase + lane * kPerLane) / P.entities_per_world, P.n_worlds - 1u) : 0u;
         if (full) transform_tile<HIER, WORLDS, CULL, true>(P, in, stage, s_bounds, small_table, wbase, first, end, world,
                                                            lane, wb, phases, meta, local);
         else transform_tile<HIER, WORLDS, CULL, false>(P, in, stage, s_bounds, small_table, wbase, first, end, world,
                                                        lane, wb, phases, meta, local);
+        if (!CULL) continue;
 
-        if (CULL) {
+        // ---- step 1 operands; park the bounds in the (drained) staging buffer ----
+        WorldBox box[kPerLane];
 #pragma unroll
-            for (int k = 0; k < kPerLane; ++k) vis[k] = 0;
-            const GlobalViews GV{ P.views + (size_t)world * F };
-            const ConstViews CV{ VS };
-            if (WORLDS) cull_views<kPerLane>(GV, F, wb, phases, vis);
-            else cull_views<kPerLane>(CV, F, wb, phases, vis);
+        for (int k = 0; k < kPerLane; ++k) {
+            box[k] = world_box(wb[k]);
+            const int idx = k * 32 + lane;
+            sb[0 * 128 + idx] = wb[k].cx; sb[1 * 128 + idx] = wb[k].cy; sb[2 * 128 + idx] = wb[k].cz;
+            sb[3 * 128 + idx] = wb[k].ex; sb[4 * 128 + idx] = wb[k].ey; sb[5 * 128 + idx] = wb[k].ez;
+            sb[6 * 128 + idx] = wb[k].r;
+            sb[7 * 128 + idx] = __uint_as_float(meta[k]);
+            sb[8 * 128 + idx] = __uint_as_float(local[k]);
+        }
+        __syncwarp();
 
-            // block-scan compaction
-            uint32_t cnt = 0;
-#pragma unroll
-            for (int k = 0; k < kPerLane; ++k) cnt += __popc(vis[k]);
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 31) s_warp_cnt[warp] = incl;
-            __syncthreads();
-            uint32_t block_total = 0, warp_off = 0;
-#pragma unroll
-            for (int w = 0; w < kWarpsPerBlock; ++w) {
-                const uint32_t c = s_warp_cnt[w];
-                if (w < warp) warp_off += c;
-                block_total += c;
+        uint32_t qcount = 0;   // warp-uniform
+
+        // One lane-per-task round: the top min(32, qcount) tasks of the queue.
+        auto task_round = [&]() {
+            const uint32_t n = qcount < 32u ? qcount : 32u;
+            const uint32_t qb = qcount - n;
+            bool alive = (uint32_t)lane < n;
+            uint32_t v = 0, idx = 0;
+            if (alive) {
+                const uint32_t t = queue[qb + lane];
+                v = t >> 8;
+                idx = t & 127u;
             }
-            if (threadIdx.x == 0 && block_total)
-                s_block_base = atomicAdd(&P.ctl->key_total, (unsigned long long)block_total);
-            __syncthreads();
-            if (warp_total) {
-                // counts: a few keys -> one shared atomic per key; many -> warp reduction per view
-                const bool sparse = !WORLDS && warp_total <= 16u;
-                if (!sparse) add_counts<kPerLane>(P, world, vis, s_counts, lane);
-                if (cnt) {
-                    const unsigned long long pos = s_block_base + warp_off + (incl - cnt);
-                    if (WORLDS) emit_keys<kPerLane>(P, GV, world, wb, vis, meta, local, pos, nullptr);
-                    else emit_keys<kPerLane>(P, CV, world, wb, vis, meta, local, pos, sparse ? s_counts : nullptr);
+            const WorldBounds w = load_bounds(sb, idx);
+            const ViewDev &sv = s_views[v];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                const float4 pl = sv.plane[p], ap = sv.aplane[p];
+                alive = alive && !(fadd(plane_dist(w, pl), plane_rad(w, ap)) < 0.0f);
+            }
+            unsigned long long key = 0;
+            if (alive) {
+                const uint32_t mt = __float_as_uint(sb[7 * 128 + idx]);
+                key = make_key(P.world_bits, 0u, v, (mt >> 11) & 255u, mt & 2047u,
+                               depth14(w, sv.depth, sv.depth_scale), __float_as_uint(sb[8 * 128 + idx]));
+                atomicAdd(&s_counts[v], 1u);
+            }
+            sink.append(alive, key);
+            qcount = qb;
+        };
+
+        for (uint32_t v = 0; v < F; ++v) {
+            bool pass[kPerLane];
+            uint32_t bal[kPerLane], n_pass = 0;
+            if (WORLDS) {
+                const GlobalViews GV{ P.views + (size_t)world * F };
+                const uint32_t mask = GV.mask(v);
+                const float4 lo = GV.lo(v), hi = GV.hi(v);
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) pass[k] = (phases[k] & mask) != 0 && box_overlaps(box[k], lo, hi);
+            } else {
+                const uint32_t mask = VS.v[v].phase_mask;
+                const float4 lo = VS.v[v].lo, hi = VS.v[v].hi;
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) pass[k] = (phases[k] & mask) != 0 && box_overlaps(box[k], lo, hi);
+            }
+#pragma unroll
+            for (int k = 0; k < kPerLane; ++k) { bal[k] = __ballot_sync(0xffffffffu, pass[k]); n_pass += __popc(bal[k]); }
+            if (n_pass == 0) continue;
+
+            if (WORLDS || n_pass >= (uint32_t)kDenseMin || v >= kSmemViews) {
+                // dense: four entities per lane, warp-uniform plane loop
+                WorldBounds w4[kPerLane];
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) w4[k] = load_bounds(sb, k * 32 + lane);
+                const GlobalViews GV{ P.views + (size_t)world * F };
+                const ConstViews CV{ VS };
+                if (WORLDS) cull_planes<kPerLane>(GV, v, w4, pass); else cull_planes<kPerLane>(CV, v, w4, pass);
+                const float4 dp = WORLDS ? GV.depth(v) : CV.depth(v);
+                const float ds = WORLDS ? GV.depth_scale(v) : CV.depth_scale(v);
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) {
+                    unsigned long long key = 0;
+                    if (pass[k]) {
+                        key = make_key(P.world_bits, world, v, (meta[k] >> 11) & 255u, meta[k] & 2047u,
+                                       depth14(w4[k], dp, ds), local[k]);
+                        if (WORLDS) atomicAdd(&P.counts[(size_t)world * F + v], 1u);
+                    }
+                    const uint32_t c = sink.append(pass[k], key);
+                    if (!WORLDS && lane == 0 && c) atomicAdd(&s_counts[v], c);
                 }
+            } else {
+                // sparse: queue (entity, view) tasks; a full round runs as soon as 32 are waiting
+                uint32_t off = qcount;
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) {
+                    if (pass[k]) queue[off + __popc(bal[k] & lt_mask)] = (unsigned short)((v << 8) | (uint32_t)(k * 32 + lane));
+                    off += __popc(bal[k]);
+                }
+                qcount = off;
+                __syncwarp();
+                while (qcount >= 32u) task_round();
             }
         }
+        if (!WORLDS) {
+            while (qcount) task_round();
+        }
+        __syncwarp();   // the staging buffer is reused by the next tile
     }
 
+    if (CULL) sink.flush();
     __syncthreads();
     if (CULL && !WORLDS && threadIdx.x < F && s_counts[threadIdx.x])
         atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);

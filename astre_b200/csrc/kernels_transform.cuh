@@ -44,7 +44,7 @@ __host__ __device__ __forceinline__ size_t tile_index(uint32_t slot, int plane)
     return (size_t)(slot >> 7) * kTileFloats + (size_t)plane * kWarpTile + (slot & 127u);
 }
 
-// One view on the device (224 B, 16-byte aligned).
+// One view on the device (256 B, 16-byte aligned).
 struct ViewDev {
     float4 plane[6];   // (nx,ny,nz,w), not normalised: left,right,bottom,top,near,far
     float4 aplane[6];  // (|nx|,|ny|,|nz|,len)
@@ -53,8 +53,9 @@ struct ViewDev {
     uint32_t phase_mask;
     uint32_t sym;      // bit i: planes 2i and 2i+1 have bit-identical (|n|, len) (orthographic pairs)
     uint32_t pad;
+    float4 lo, hi;     // world-space box around the view volume (xyz)
 };
-static_assert(sizeof(ViewDev) == 224, "ViewDev layout");
+static_assert(sizeof(ViewDev) == 256, "ViewDev layout");
 
 struct BoundsDev {   // 32 B; extents and radius are >= 0 (checked by astre_gpu_set_mesh_bounds)
     float cx, cy, cz, ex;
@@ -94,9 +95,7 @@ __device__ __forceinline__ uint32_t u4get(const uint4 &v, int k)
 }
 
 // World-space bounds (spec; the CPU checker restates it).
-// rho is NOT part of the spec: an upper bound (with margin) on the support
-// radius per unit plane length, used only to skip work whose outcome is certain.
-struct WorldBounds { float cx, cy, cz, ex, ey, ez, r, rho; };
+struct WorldBounds { float cx, cy, cz, ex, ey, ez, r; };
 
 __device__ __forceinline__ WorldBounds world_bounds(const float (&m)[16], const BoundsDev &b)
 {
@@ -111,11 +110,25 @@ __device__ __forceinline__ WorldBounds world_bounds(const float (&m)[16], const 
     const float l1 = ffma(m[4], m[4], ffma(m[5], m[5], fmul(m[6], m[6])));
     const float l2 = ffma(m[8], m[8], ffma(m[9], m[9], fmul(m[10], m[10])));
     w.r = fmul(b.r, __fsqrt_rn(fmaxf(fmaxf(l0, l1), l2)));
-    // |n|.e' + r'*len <= len*(ex+ey+ez+r') because every |n_i| <= len; 1.0001 and
-    // 1e-20 swallow the (< 2^-20 relative, few-ulp-of-denormal absolute) rounding
-    // of both sides.
-    w.rho = ffma(fadd(fadd(fadd(w.ex, w.ey), w.ez), w.r), 1.0001f, 1e-20f);
     return w;
+}
+
+// Axis-aligned box of the bounds: c -+ (e + r) per axis.
+struct WorldBox { float lx, ly, lz, hx, hy, hz; };
+
+__device__ __forceinline__ WorldBox world_box(const WorldBounds &w)
+{
+    const float tx = fadd(w.ex, w.r), ty = fadd(w.ey, w.r), tz = fadd(w.ez, w.r);
+    WorldBox b;
+    b.lx = fsub(w.cx, tx); b.ly = fsub(w.cy, ty); b.lz = fsub(w.cz, tz);
+    b.hx = fadd(w.cx, tx); b.hy = fadd(w.cy, ty); b.hz = fadd(w.cz, tz);
+    return b;
+}
+
+// Spec step 1: the bounds' box must overlap the view's box (false on NaN = keep).
+__device__ __forceinline__ bool box_overlaps(const WorldBox &b, const float4 &lo, const float4 &hi)
+{
+    return !(b.hx < lo.x) && !(b.lx > hi.x) && !(b.hy < lo.y) && !(b.ly > hi.y) && !(b.hz < lo.z) && !(b.lz > hi.z);
 }
 
 __device__ __forceinline__ float plane_dist(const WorldBounds &w, const float4 &pl)
@@ -172,6 +185,8 @@ struct ConstViews {
     __device__ __forceinline__ float depth_scale(uint32_t v) const { return vs.v[v].depth_scale; }
     __device__ __forceinline__ uint32_t mask(uint32_t v) const { return vs.v[v].phase_mask; }
     __device__ __forceinline__ uint32_t sym(uint32_t v) const { return vs.v[v].sym; }
+    __device__ __forceinline__ float4 lo(uint32_t v) const { return vs.v[v].lo; }
+    __device__ __forceinline__ float4 hi(uint32_t v) const { return vs.v[v].hi; }
 };
 struct GlobalViews {
     const ViewDev *vw;
@@ -181,48 +196,56 @@ struct GlobalViews {
     __device__ __forceinline__ float depth_scale(uint32_t v) const { return __ldg(&vw[v].depth_scale); }
     __device__ __forceinline__ uint32_t mask(uint32_t v) const { return __ldg(&vw[v].phase_mask); }
     __device__ __forceinline__ uint32_t sym(uint32_t v) const { return __ldg(&vw[v].sym); }
+    __device__ __forceinline__ float4 lo(uint32_t v) const { return __ldg(&vw[v].lo); }
+    __device__ __forceinline__ float4 hi(uint32_t v) const { return __ldg(&vw[v].hi); }
 };
 
-// Tests the K entities of one lane against the F views of their world; vis[k]
-// gets bit v when entity k passes view v.  Specification per plane: reject iff
-// dist + rad < 0.  Evaluation: dist first; dist >= 0 cannot be rejected (rad >= 0),
-// dist + rho*len < 0 is certainly rejected (rho*len >= rad), and only when some
-// lane of the warp falls between the two is rad computed (exactly as specified).
-// The plane loop leaves as soon as no lane of the warp has a survivor.
+// Spec step 2 for one view: the six plane tests (reject iff dist + rad < 0) on the
+// K entities of one lane; alive[] holds the survivors of step 1 on entry and of
+// both steps on exit.  Orthographic pairs share their support radius (sym).
+// Leaves as soon as no lane of the warp has a survivor (warp-uniform branch).
+template <int K, class Views>
+__device__ __forceinline__ void cull_planes(const Views &V, const uint32_t v, const WorldBounds (&wb)[K], bool (&alive)[K])
+{
+    const uint32_t sym = V.sym(v);
+    float rad[K];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const float4 pl = V.plane(v, p);
+        if (!((p & 1) && ((sym >> (p >> 1)) & 1u))) {
+            const float4 ap = V.aplane(v, p);
+#pragma unroll
+            for (int k = 0; k < K; ++k) rad[k] = plane_rad(wb[k], ap);
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            alive[k] = alive[k] && !(fadd(plane_dist(wb[k], pl), rad[k]) < 0.0f);
+            any |= alive[k];
+        }
+        if (p < 5 && !__any_sync(0xffffffffu, any)) break;
+    }
+}
+
+// Both steps over all F views (batched-worlds and indexed paths); vis[k] gets bit v.
 template <int K, class Views>
 __device__ __forceinline__ void cull_views(const Views &V, const uint32_t F, const WorldBounds (&wb)[K],
                                            const uint32_t (&phases)[K], uint32_t (&vis)[K])
 {
+    WorldBox box[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) box[k] = world_box(wb[k]);
     for (uint32_t v = 0; v < F; ++v) {
         const uint32_t mask = V.mask(v);
+        const float4 lo = V.lo(v), hi = V.hi(v);
         bool alive[K], any = false;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { alive[k] = (phases[k] & mask) != 0; any |= alive[k]; }
-        if (!__any_sync(0xffffffffu, any)) continue;
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-            const float4 pl = V.plane(v, p);
-            const float len = V.aplane(v, p).w;
-            float d[K];
-            bool band = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                d[k] = plane_dist(wb[k], pl);
-                const bool out = ffma(wb[k].rho, len, d[k]) < 0.0f;     // certain reject
-                alive[k] = alive[k] && !out;
-                band |= alive[k] && !(d[k] >= 0.0f);                    // undecided (includes NaN)
-            }
-            if (__any_sync(0xffffffffu, band)) {
-                const float4 ap = V.aplane(v, p);
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    alive[k] = alive[k] && !(fadd(d[k], plane_rad(wb[k], ap)) < 0.0f);
-            }
-            any = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) any |= alive[k];
-            if (p < 5 && !__any_sync(0xffffffffu, any)) break;
+        for (int k = 0; k < K; ++k) {
+            alive[k] = (phases[k] & mask) != 0 && box_overlaps(box[k], lo, hi);
+            any |= alive[k];
         }
+        if (!__any_sync(0xffffffffu, any)) continue;
+        cull_planes<K>(V, v, wb, alive);
 #pragma unroll
         for (int k = 0; k < K; ++k) vis[k] |= (alive[k] ? 1u : 0u) << v;
     }

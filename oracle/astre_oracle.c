@@ -66,6 +66,8 @@ typedef struct {
     float depth_scale;   /* 16384 / (distance between near and far planes) */
     uint32_t phase_mask; /* RenderPhase bits this view draws */
     uint32_t pad[2];
+    float lo[4];         /* world-space box around the view volume (xyz; w unused) */
+    float hi[4];
 } orc_view;
 
 /* ---- GLM 1.0.1 restatements ---------------------------------------------- */
@@ -357,6 +359,58 @@ ORC_API int orc_transform_hierarchy(uint32_t n, const float *pos3, const float *
 
 /* ---- a10: views, bounds, cull, keys, sort (spec-defined, Appendix B) ------- */
 
+/* World-space axis-aligned box around the view volume: the eight NDC corners
+ * (+-1,+-1,+-1) taken through the inverse clip matrix in double precision,
+ * widened by 1e-4 of its size + 1e-6, then rounded outwards to float.  A
+ * singular matrix or a corner with w <= 0 gives the unbounded box.  (Spec: the
+ * box test removes the classic plane-test false positives beyond the corners
+ * of the volume.) */
+static void view_box(const float *clip16, float *lo4, float *hi4)
+{
+    double m[16], inv[16];
+    for (int i = 0; i < 16; ++i) m[i] = (double)clip16[i];
+    inv[0]  =  m[5]*m[10]*m[15] - m[5]*m[11]*m[14] - m[9]*m[6]*m[15] + m[9]*m[7]*m[14] + m[13]*m[6]*m[11] - m[13]*m[7]*m[10];
+    inv[4]  = -m[4]*m[10]*m[15] + m[4]*m[11]*m[14] + m[8]*m[6]*m[15] - m[8]*m[7]*m[14] - m[12]*m[6]*m[11] + m[12]*m[7]*m[10];
+    inv[8]  =  m[4]*m[9]*m[15]  - m[4]*m[11]*m[13] - m[8]*m[5]*m[15] + m[8]*m[7]*m[13] + m[12]*m[5]*m[11] - m[12]*m[7]*m[9];
+    inv[12] = -m[4]*m[9]*m[14]  + m[4]*m[10]*m[13] + m[8]*m[5]*m[14] - m[8]*m[6]*m[13] - m[12]*m[5]*m[10] + m[12]*m[6]*m[9];
+    inv[1]  = -m[1]*m[10]*m[15] + m[1]*m[11]*m[14] + m[9]*m[2]*m[15] - m[9]*m[3]*m[14] - m[13]*m[2]*m[11] + m[13]*m[3]*m[10];
+    inv[5]  =  m[0]*m[10]*m[15] - m[0]*m[11]*m[14] - m[8]*m[2]*m[15] + m[8]*m[3]*m[14] + m[12]*m[2]*m[11] - m[12]*m[3]*m[10];
+    inv[9]  = -m[0]*m[9]*m[15]  + m[0]*m[11]*m[13] + m[8]*m[1]*m[15] - m[8]*m[3]*m[13] - m[12]*m[1]*m[11] + m[12]*m[3]*m[9];
+    inv[13] =  m[0]*m[9]*m[14]  - m[0]*m[10]*m[13] - m[8]*m[1]*m[14] + m[8]*m[2]*m[13] + m[12]*m[1]*m[10] - m[12]*m[2]*m[9];
+    inv[2]  =  m[1]*m[6]*m[15]  - m[1]*m[7]*m[14]  - m[5]*m[2]*m[15] + m[5]*m[3]*m[14] + m[13]*m[2]*m[7]  - m[13]*m[3]*m[6];
+    inv[6]  = -m[0]*m[6]*m[15]  + m[0]*m[7]*m[14]  + m[4]*m[2]*m[15] - m[4]*m[3]*m[14] - m[12]*m[2]*m[7]  + m[12]*m[3]*m[6];
+    inv[10] =  m[0]*m[5]*m[15]  - m[0]*m[7]*m[13]  - m[4]*m[1]*m[15] + m[4]*m[3]*m[13] + m[12]*m[1]*m[7]  - m[12]*m[3]*m[5];
+    inv[14] = -m[0]*m[5]*m[14]  + m[0]*m[6]*m[13]  + m[4]*m[1]*m[14] - m[4]*m[2]*m[13] - m[12]*m[1]*m[6]  + m[12]*m[2]*m[5];
+    inv[3]  = -m[1]*m[6]*m[11]  + m[1]*m[7]*m[10]  + m[5]*m[2]*m[11] - m[5]*m[3]*m[10] - m[9]*m[2]*m[7]   + m[9]*m[3]*m[6];
+    inv[7]  =  m[0]*m[6]*m[11]  - m[0]*m[7]*m[10]  - m[4]*m[2]*m[11] + m[4]*m[3]*m[10] + m[8]*m[2]*m[7]   - m[8]*m[3]*m[6];
+    inv[11] = -m[0]*m[5]*m[11]  + m[0]*m[7]*m[9]   + m[4]*m[1]*m[11] - m[4]*m[3]*m[9]  - m[8]*m[1]*m[7]   + m[8]*m[3]*m[5];
+    inv[15] =  m[0]*m[5]*m[10]  - m[0]*m[6]*m[9]   - m[4]*m[1]*m[10] + m[4]*m[2]*m[9]  + m[8]*m[1]*m[6]   - m[8]*m[2]*m[5];
+    const double det = m[0]*inv[0] + m[1]*inv[4] + m[2]*inv[8] + m[3]*inv[12];
+    int ok = (det != 0.0) && isfinite(det);
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int c = 0; c < 8 && ok; ++c) {
+        const double x = (c & 1) ? 1.0 : -1.0, y = (c & 2) ? 1.0 : -1.0, z = (c & 4) ? 1.0 : -1.0;
+        /* adj * (x,y,z,1); the common 1/det cancels in the divide but fixes the sign of w */
+        const double w = (inv[3]*x + inv[7]*y + inv[11]*z + inv[15]) / det;
+        if (!(w > 0.0) || !isfinite(w)) { ok = 0; break; }
+        const double p[3] = { (inv[0]*x + inv[4]*y + inv[8]*z  + inv[12]) / det / w,
+                              (inv[1]*x + inv[5]*y + inv[9]*z  + inv[13]) / det / w,
+                              (inv[2]*x + inv[6]*y + inv[10]*z + inv[14]) / det / w };
+        for (int i = 0; i < 3; ++i) {
+            if (!isfinite(p[i])) ok = 0;
+            if (p[i] < lo[i]) lo[i] = p[i];
+            if (p[i] > hi[i]) hi[i] = p[i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (!ok) { lo4[i] = -INFINITY; hi4[i] = INFINITY; continue; }
+        const double d = (hi[i] - lo[i]) * 1e-4 + 1e-6;
+        lo4[i] = nextafterf((float)(lo[i] - d), -INFINITY);
+        hi4[i] = nextafterf((float)(hi[i] + d), INFINITY);
+    }
+    lo4[3] = 0.0f; hi4[3] = 0.0f;
+}
+
 /* Planes from clip = P*V (GL clip volume -w <= x,y,z <= w), column-major input. */
 ORC_API void orc_extract_view(const float *clip16, uint32_t phase_mask, orc_view *v)
 {
@@ -388,6 +442,7 @@ ORC_API void orc_extract_view(const float *clip16, uint32_t phase_mask, orc_view
     v->depth_scale = (range > 0.0f && scale < INFINITY) ? scale : 0.0f;
     v->phase_mask = phase_mask;
     v->pad[0] = v->pad[1] = 0;
+    view_box(clip16, v->lo, v->hi);
 }
 
 /* key = world(Wb) | view(5) | shader(8) | mesh(11) | depth(14) | local slot(26-Wb),
@@ -430,10 +485,16 @@ static inline void world_bounds_of(const float *m, const orc_bounds *b, world_bo
     wb->r = b->radius * sqrtf(mx);
 }
 
-/* Returns 1 if the bounds are inside or intersect all six planes.  A NaN never
- * culls (the comparison is false on unordered operands). */
+/* Returns 1 if the bounds overlap the view's world-space box and are inside or
+ * intersect all six planes.  A NaN never culls (the comparisons are false on
+ * unordered operands). */
 static inline int inside_view(const world_bounds *wb, const orc_view *v)
 {
+    for (int i = 0; i < 3; ++i) {
+        const float t = wb->e[i] + wb->r;
+        if (wb->c[i] + t < v->lo[i]) return 0;
+        if (wb->c[i] - t > v->hi[i]) return 0;
+    }
     for (int p = 0; p < 6; ++p) {
         const float *pl = v->plane[p], *ap = v->aplane[p];
         float dist = fmaf(pl[0], wb->c[0], fmaf(pl[1], wb->c[1], fmaf(pl[2], wb->c[2], pl[3])));

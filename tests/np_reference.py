@@ -74,6 +74,54 @@ def hierarchy(pos, rot, scale, parent):
     return world
 
 
+def view_box(clip):
+    """World-space box of the view volume; same formula order as the specification (doubles)."""
+    m = [float(x) for x in clip]
+    a = [0.0] * 16
+    a[0]  =  m[5]*m[10]*m[15] - m[5]*m[11]*m[14] - m[9]*m[6]*m[15] + m[9]*m[7]*m[14] + m[13]*m[6]*m[11] - m[13]*m[7]*m[10]
+    a[4]  = -m[4]*m[10]*m[15] + m[4]*m[11]*m[14] + m[8]*m[6]*m[15] - m[8]*m[7]*m[14] - m[12]*m[6]*m[11] + m[12]*m[7]*m[10]
+    a[8]  =  m[4]*m[9]*m[15]  - m[4]*m[11]*m[13] - m[8]*m[5]*m[15] + m[8]*m[7]*m[13] + m[12]*m[5]*m[11] - m[12]*m[7]*m[9]
+    a[12] = -m[4]*m[9]*m[14]  + m[4]*m[10]*m[13] + m[8]*m[5]*m[14] - m[8]*m[6]*m[13] - m[12]*m[5]*m[10] + m[12]*m[6]*m[9]
+    a[1]  = -m[1]*m[10]*m[15] + m[1]*m[11]*m[14] + m[9]*m[2]*m[15] - m[9]*m[3]*m[14] - m[13]*m[2]*m[11] + m[13]*m[3]*m[10]
+    a[5]  =  m[0]*m[10]*m[15] - m[0]*m[11]*m[14] - m[8]*m[2]*m[15] + m[8]*m[3]*m[14] + m[12]*m[2]*m[11] - m[12]*m[3]*m[10]
+    a[9]  = -m[0]*m[9]*m[15]  + m[0]*m[11]*m[13] + m[8]*m[1]*m[15] - m[8]*m[3]*m[13] - m[12]*m[1]*m[11] + m[12]*m[3]*m[9]
+    a[13] =  m[0]*m[9]*m[14]  - m[0]*m[10]*m[13] - m[8]*m[1]*m[14] + m[8]*m[2]*m[13] + m[12]*m[1]*m[10] - m[12]*m[2]*m[9]
+    a[2]  =  m[1]*m[6]*m[15]  - m[1]*m[7]*m[14]  - m[5]*m[2]*m[15] + m[5]*m[3]*m[14] + m[13]*m[2]*m[7]  - m[13]*m[3]*m[6]
+    a[6]  = -m[0]*m[6]*m[15]  + m[0]*m[7]*m[14]  + m[4]*m[2]*m[15] - m[4]*m[3]*m[14] - m[12]*m[2]*m[7]  + m[12]*m[3]*m[6]
+    a[10] =  m[0]*m[5]*m[15]  - m[0]*m[7]*m[13]  - m[4]*m[1]*m[15] + m[4]*m[3]*m[13] + m[12]*m[1]*m[7]  - m[12]*m[3]*m[5]
+    a[14] = -m[0]*m[5]*m[14]  + m[0]*m[6]*m[13]  + m[4]*m[1]*m[14] - m[4]*m[2]*m[13] - m[12]*m[1]*m[6]  + m[12]*m[2]*m[5]
+    a[3]  = -m[1]*m[6]*m[11]  + m[1]*m[7]*m[10]  + m[5]*m[2]*m[11] - m[5]*m[3]*m[10] - m[9]*m[2]*m[7]   + m[9]*m[3]*m[6]
+    a[7]  =  m[0]*m[6]*m[11]  - m[0]*m[7]*m[10]  - m[4]*m[2]*m[11] + m[4]*m[3]*m[10] + m[8]*m[2]*m[7]   - m[8]*m[3]*m[6]
+    a[11] = -m[0]*m[5]*m[11]  + m[0]*m[7]*m[9]   + m[4]*m[1]*m[11] - m[4]*m[3]*m[9]  - m[8]*m[1]*m[7]   + m[8]*m[3]*m[5]
+    a[15] =  m[0]*m[5]*m[10]  - m[0]*m[6]*m[9]   - m[4]*m[1]*m[10] + m[4]*m[2]*m[9]  + m[8]*m[1]*m[6]   - m[8]*m[2]*m[5]
+    det = m[0]*a[0] + m[1]*a[4] + m[2]*a[8] + m[3]*a[12]
+    inf = float("inf")
+    ok = det != 0.0 and np.isfinite(det)
+    lo, hi = [inf] * 3, [-inf] * 3
+    for c in range(8):
+        if not ok:
+            break
+        x, y, z = (1.0 if c & 1 else -1.0), (1.0 if c & 2 else -1.0), (1.0 if c & 4 else -1.0)
+        w = (a[3]*x + a[7]*y + a[11]*z + a[15]) / det
+        if not (w > 0.0) or not np.isfinite(w):
+            ok = False
+            break
+        p = [(a[0]*x + a[4]*y + a[8]*z + a[12]) / det / w, (a[1]*x + a[5]*y + a[9]*z + a[13]) / det / w,
+             (a[2]*x + a[6]*y + a[10]*z + a[14]) / det / w]
+        for i in range(3):
+            if not np.isfinite(p[i]):
+                ok = False
+            lo[i], hi[i] = min(lo[i], p[i]), max(hi[i], p[i])
+    if not ok:
+        return np.full(3, -np.inf, f32), np.full(3, np.inf, f32)
+    out_lo, out_hi = np.empty(3, f32), np.empty(3, f32)
+    for i in range(3):
+        d = (hi[i] - lo[i]) * 1e-4 + 1e-6
+        out_lo[i] = np.nextafter(f32(lo[i] - d), f32(-np.inf))
+        out_hi[i] = np.nextafter(f32(hi[i] + d), f32(np.inf))
+    return out_lo, out_hi
+
+
 def extract_view(clip):
     row = [np.array([clip[k * 4 + i] for k in range(4)], f32) for i in range(4)]
     planes = np.stack([row[3] + row[0], row[3] - row[0], row[3] + row[1], row[3] - row[1],
@@ -111,9 +159,14 @@ def cull_keys(world, mesh, shader, flags, bounds, clip, masks, n_worlds=1, epw=0
         sel_w = world_of == w
         for v in range(F):
             planes, aplanes, length, depth, scale = extract_view(clip[w, v])
+            box_lo, box_hi = view_box(clip[w, v])
             part = ((flags & 1) != 0) & ((((flags >> 1) & 15) & int(masks[v])) != 0) & valid & sel_w
             inside = part.copy()
             with np.errstate(all="ignore"):
+                for i in range(3):
+                    t = e[i] + r
+                    inside &= ~((c[i] + t) < box_lo[i])
+                    inside &= ~((c[i] - t) > box_hi[i])
                 for p in range(6):
                     bc = lambda s: np.full(n, s, f32)
                     dist = fma(bc(planes[p, 0]), c[0], fma(bc(planes[p, 1]), c[1], fma(bc(planes[p, 2]), c[2], bc(planes[p, 3]))))

@@ -22,7 +22,8 @@ class Bounds(C.Structure):
 
 class View(C.Structure):
     _fields_ = [("plane", (C.c_float * 4) * 6), ("aplane", (C.c_float * 4) * 6), ("depth", C.c_float * 4),
-                ("depth_scale", C.c_float), ("phase_mask", C.c_uint32), ("pad", C.c_uint32 * 2)]
+                ("depth_scale", C.c_float), ("phase_mask", C.c_uint32), ("pad", C.c_uint32 * 2),
+                ("lo", C.c_float * 4), ("hi", C.c_float * 4)]
 
 
 def build():
