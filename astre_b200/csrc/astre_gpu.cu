@@ -62,6 +62,11 @@ struct astre_gpu_ctx {
     uint32_t cap_counts = 0;
     FrameControl *d_ctl = nullptr;
     SortControl *d_sc = nullptr;
+    uint32_t *d_block_hist = nullptr;
+    uint32_t *d_sort_table = nullptr;     // cooperative sort: [tiles][256] counts/prefixes, then 256 totals, then the barrier word
+    uint64_t sort_table_tiles = 0;
+    int coop_grid = 0;                    // co-resident CTAs of k_sort_coop
+    int sort_mode = 0;                    // 0 auto, 1 cooperative, 2 onesweep (ASTRE_SORT)
     unsigned long long *d_lookback = nullptr;
     float4 *d_gather = nullptr;
     uint64_t cap_gather = 0;
@@ -81,7 +86,7 @@ struct astre_gpu_ctx {
     std::vector<uint64_t> h_entity_id;
 
     // cached read-backs of the last frame
-    bool frame_done = false, results_cached = false;
+    bool frame_done = false, results_cached = false, results_cached_total_valid = false;
     uint32_t last_flags = 0;
     std::vector<uint32_t> h_counts;
     std::vector<unsigned long long> h_offsets;
@@ -154,10 +159,9 @@ __global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *coun
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         ctl->key_total = 0; ctl->overflow = 0; ctl->pad = 0;
-        sc->result_buf = 0; sc->n_keys = 0; sc->epoch = epoch;
+        ctl->or_lo = 0; ctl->or_hi = 0; ctl->and_lo = 0xFFFFFFFFu; ctl->and_hi = 0xFFFFFFFFu;
+        sc->result_buf = 0; sc->n_keys = 0; sc->n_passes = 0; sc->epoch = epoch;
     }
-    for (uint32_t i = tid; i < kSortPasses * 256; i += nth) (&sc->hist[0][0])[i] = 0;
-    for (uint32_t i = tid; i < kSortPasses; i += nth) { sc->skip[i] = 1; sc->src[i] = 0; sc->tile_counter[i] = 0; }
     for (uint32_t i = tid; i < n_counts; i += nth) counts[i] = 0;
 }
 
@@ -249,12 +253,11 @@ int cache_results(astre_gpu_ctx *ctx)
     cudaStream_t s = ctx->last_stream;
     const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
     FrameControl ctl;
-    SortControl *sc_host = nullptr;
     CK(cudaStreamSynchronize(s));
     CK(cudaMemcpy(&ctl, ctx->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     uint32_t result_buf = 0;
-    CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    (void)sc_host;
+    if (ctx->last_flags & ASTRE_FRAME_SORT)
+        CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     ctx->h_counts.assign(n_counts, 0);
     ctx->h_offsets.assign((size_t)n_counts + 1, 0);
     if (n_counts) {
@@ -266,6 +269,7 @@ int cache_results(astre_gpu_ctx *ctx)
     ctx->h_overflow = (ctl.key_total > ctx->max_keys) ? 1u : ctl.overflow;
     ctx->h_result_buf = result_buf;
     ctx->results_cached = true;
+    ctx->results_cached_total_valid = true;
     return ASTRE_OK;
 }
 
@@ -351,9 +355,22 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaMemset(ctx->d_ctl, 0, sizeof(FrameControl)));
     CKC(cudaMalloc(&ctx->d_sc, sizeof(SortControl)));
     CKC(cudaMemset(ctx->d_sc, 0, sizeof(SortControl)));
+    CKC(cudaMalloc(&ctx->d_block_hist, (size_t)kHistBlocks * kSortPasses * 256 * sizeof(uint32_t)));
     const size_t n_sort_tiles = (size_t)((ctx->max_keys + kSortTile - 1) / kSortTile) + 1;
     CKC(cudaMalloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
     CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
+    ctx->sort_table_tiles = n_sort_tiles;
+    CKC(cudaMalloc(&ctx->d_sort_table, (n_sort_tiles * 256 + 256 + 32) * sizeof(uint32_t)));
+    {
+        int coop = 0, occ_sort = 0;
+        CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_coop, kSortThreads, 0));
+        ctx->coop_grid = coop ? ctx->sm_count * std::min(occ_sort, 2) : 0;
+        if (const char *m = std::getenv("ASTRE_SORT")) {
+            if (!std::strcmp(m, "coop")) ctx->sort_mode = 1;
+            else if (!std::strcmp(m, "onesweep")) ctx->sort_mode = 2;
+        }
+    }
     CKC(cudaEventCreate(&ctx->ev_begin));
     CKC(cudaEventCreate(&ctx->ev_cull0));
     CKC(cudaEventCreate(&ctx->ev_cull1));
@@ -381,7 +398,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots };
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_sort_table };
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -662,18 +679,34 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     }
 
     if (sort) {
-        const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
-        k_sort_hist<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_ctl, ctx->max_keys, ctx->d_sc);
-        CK_LAUNCH();
-        k_sort_plan<<<1, kSortPasses * 32, 0, s>>>(ctx->d_ctl, ctx->max_keys, ctx->d_sc);
-        CK_LAUNCH();
-        for (int p = 0; p < kSortPasses; ++p) {
-            k_sort_pass<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, p);
+        // ASTRE_SORT=coop selects the cooperative single-launch sort (both sorts are correct for any count).
+        // (measured r1: the cooperative sort is not yet faster than onesweep at 0.7M keys, so it is opt-in)
+        bool coop = ctx->sort_mode == 1 && ctx->coop_grid > 0;
+        if (coop) {
+            uint32_t *table = ctx->d_sort_table;
+            uint32_t *totals = table + ctx->sort_table_tiles * 256;
+            uint32_t *barrier = totals + 256;
+            CK(cudaMemsetAsync(barrier, 0, sizeof(uint32_t), s));
+            unsigned long long cap = ctx->max_keys;
+            void *args[] = { &ctx->d_keys[0], &ctx->d_keys[1], &ctx->d_ctl, &cap, &ctx->d_sc, &table, &totals, &barrier };
+            CK(cudaLaunchCooperativeKernel((const void *)k_sort_coop, dim3(ctx->coop_grid), dim3(kSortThreads), args, 0, s));
             CK_LAUNCH();
+        } else {
+            const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
+            k_sort_plan<<<1, 32, 0, s>>>(ctx->d_ctl, ctx->max_keys, ctx->d_sc);
+            CK_LAUNCH();
+            k_sort_hist<<<kHistBlocks, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_sc, ctx->d_block_hist);
+            CK_LAUNCH();
+            k_sort_scan<<<kSortPasses, 256, 0, s>>>(ctx->d_sc, ctx->d_block_hist, kHistBlocks);
+            CK_LAUNCH();
+            for (int p = 0; p < kSortPasses; ++p) {
+                k_sort_pass<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, p);
+                CK_LAUNCH();
+            }
         }
     }
     if (n_counts) {
-        k_scan_counts<<<1, 1024, 0, s>>>(ctx->d_counts, ctx->d_offsets, n_counts);
+        k_scan_counts<<<1, 256, 0, s>>>(ctx->d_counts, ctx->d_offsets, n_counts);
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ctx->ev_end, s));

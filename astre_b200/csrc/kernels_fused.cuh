@@ -89,10 +89,19 @@ struct KeySink {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&P->ctl->key_total, (unsigned long long)fill);
             base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long o = 0ull, a = ~0ull;
             for (uint32_t i = lane; i < fill; i += 32) {
-                const unsigned long long pos = base + i;
-                if (pos < P->key_cap) P->keys[pos] = kbuf[i];
+                const unsigned long long k = kbuf[i], pos = base + i;
+                o |= k; a &= k;
+                if (pos < P->key_cap) P->keys[pos] = k;
                 else P->ctl->overflow = 1u;
+            }
+            // the sort only looks at key bits that differ: feed the frame-wide OR / AND
+            const uint32_t olo = __reduce_or_sync(0xffffffffu, (uint32_t)o), ohi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
+            const uint32_t alo = __reduce_and_sync(0xffffffffu, (uint32_t)a), ahi = __reduce_and_sync(0xffffffffu, (uint32_t)(a >> 32));
+            if (lane == 0) {
+                atomicOr(&P->ctl->or_lo, olo); atomicOr(&P->ctl->or_hi, ohi);
+                atomicAnd(&P->ctl->and_lo, alo); atomicAnd(&P->ctl->and_hi, ahi);
             }
         }
         __syncwarp();

@@ -63,10 +63,12 @@ struct BoundsDev {   // 32 B; extents and radius are >= 0 (checked by astre_gpu_
     uint32_t reserved;
 };
 
-struct FrameControl {            // one per context, zeroed at the start of a frame
+struct FrameControl {            // one per context, reset at the start of a frame
     unsigned long long key_total; // keys reserved so far (may exceed capacity)
     uint32_t overflow;
     uint32_t pad;
+    uint32_t or_lo, or_hi;        // OR of all keys emitted
+    uint32_t and_lo, and_hi;      // AND of all keys emitted (starts all-ones)
 };
 
 struct FrameParams {
@@ -270,6 +272,8 @@ __device__ __forceinline__ void emit_keys(const FrameParams &P, const Views &V, 
             if (pos < P.key_cap) P.keys[pos] = key;
             else P.ctl->overflow = 1u;
             ++pos;
+            atomicOr(&P.ctl->or_lo, (uint32_t)key); atomicOr(&P.ctl->or_hi, (uint32_t)(key >> 32));
+            atomicAnd(&P.ctl->and_lo, (uint32_t)key); atomicAnd(&P.ctl->and_hi, (uint32_t)(key >> 32));
             if (s_counts) atomicAdd(&s_counts[v], 1u);
         }
     }
