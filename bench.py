@@ -206,18 +206,17 @@ def main():
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    counts_dev = torch.zeros(F, dtype=torch.int32, device="cuda")
-    all_counts = torch.zeros(world * F, dtype=torch.int32, device="cuda") if world > 1 else None
-    counts_ptr = ctx.device_counts_ptr()
-    lib = ctx._lib
-    cudart = torch.cuda.cudart()
+    from astre_b200 import multi
+
+    class _DeviceCounts:      # zero-copy torch view of the library's per-view counters
+        __cuda_array_interface__ = {"shape": (F,), "typestr": "<i4", "data": (ctx.device_counts_ptr(), False), "version": 2}
+    counts_dev = torch.as_tensor(_DeviceCounts(), device="cuda")
 
     def step():
         ctx.frame(gpu.FRAME_ALL)
         if world > 1:
-            # per-shard visible counts -> every rank (the only exchange on the path)
-            cudart.cudaMemcpyAsync(counts_dev.data_ptr(), counts_ptr, F * 4, 3, stream.cuda_stream)
-            dist.all_gather_into_tensor(all_counts, counts_dev)
+            # per-shard visible counts -> every rank: the only exchange on the path (NCCL all-gather)
+            multi.exchange_counts(counts_dev)
 
     def barrier():
         if world > 1:

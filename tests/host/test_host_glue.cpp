@@ -1,0 +1,282 @@
+// Tests of the engine-side glue (astre_b200/host) in the style of the reference's gtest
+// suite (engine/tests): build a small world like game/resources/worlds/levels/level_0.json,
+// run the systems, compare with the CPU oracle.  `--cpu` runs only the checks that need no device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../astre_b200/host/astre_host.hpp"
+
+using namespace astre::gpu;
+
+extern "C" {
+struct orc_bounds { float center[3], extent[3], radius; uint32_t reserved; };
+struct orc_view { float plane[6][4], aplane[6][4], depth[4], depth_scale; uint32_t phase_mask, pad[2]; float lo[4], hi[4]; };
+void orc_trs_matrix(const float *pos, const float *rot, const float *scl, float *out16);
+void orc_basis(const float *rot, float *fwd, float *up, float *right);
+void orc_camera_view_proj(const float *pos, const float *fwd, const float *up, float fov, float aspect, float zn, float zf,
+                          float *view16, float *proj16);
+int orc_light_space(const float *pos3, const float *dir3, int type, float outer_cutoff, float *out16);
+void orc_mat4_mul(const float *a, const float *b, float *out);
+void orc_extract_view(const float *clip16, uint32_t phase_mask, orc_view *v);
+uint64_t orc_frame(uint32_t n, const float *pos3, const float *rot4, const float *scl3, const uint32_t *parent,
+                   const uint32_t *mesh_id, const uint32_t *shader_id, const uint8_t *flags, const orc_bounds *bounds,
+                   uint32_t n_meshes, uint32_t n_worlds, uint32_t epw, uint32_t vpw, const orc_view *views, float *world16,
+                   uint64_t *keys, uint64_t cap, uint32_t *counts);
+}
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT(cond)                                                                          \
+    do {                                                                                      \
+        ++g_checks;                                                                           \
+        if (!(cond)) { ++g_failures; std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); } \
+    } while (0)
+
+static bool same_bits(const float *a, const float *b, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        if (std::isnan(a[i]) && std::isnan(b[i])) continue;
+        if (std::memcmp(&a[i], &b[i], 4) != 0) return false;
+    }
+    return true;
+}
+
+struct Names : IResourceNames {   // stands in for IRenderer's name tables
+    std::optional<std::size_t> getVertexBuffer(const std::string &n) const override
+    {
+        static const char *k[] = {"cube_prefab", "quad_prefab", "cone_prefab", "cylinder_prefab",
+                                  "icosphere1_prefab", "icosphere2_prefab", "icosphere3_prefab", "dome_prefab"};
+        for (std::size_t i = 0; i < 8; ++i) if (n == k[i]) return i;
+        return std::nullopt;
+    }
+    std::optional<std::size_t> getShader(const std::string &n) const override
+    {
+        if (n == "deferred_shader") return 0;
+        if (n == "basic_shader") return 1;
+        return std::nullopt;
+    }
+};
+
+static const astre_mesh_bounds kBounds[8] = {
+    {{0, 0, 0}, {0.5f, 0.5f, 0.5f}, 0, 0}, {{0, 0, 0}, {0.5f, 0.5f, 0}, 0, 0}, {{0, 0, 0}, {0.5f, 0.5f, 0.5f}, 0, 0},
+    {{0, 0, 0}, {0.5f, 0.5f, 0.5f}, 0, 0}, {{0, 0, 0}, {0, 0, 0}, 1, 0},       {{0, 0, 0}, {0, 0, 0}, 1, 0},
+    {{0, 0, 0}, {0, 0, 0}, 1, 0},          {{0, 0, 0}, {0, 0, 0}, 1, 0}};
+
+static void test_mirror_cpu()
+{
+    Names names;
+    EntityMirror m(8);
+    TransformComponent t;
+    t.position = Vec3{1, 2, 3};
+    VisualComponent v;
+    v.vertex_buffer_name = "cube_prefab"; v.shader_name = "deferred_shader";
+    EXPECT(m.spawn(10, t, &v, &names) == 0);
+    EXPECT(m.spawn(11, t, nullptr, nullptr) == 1);
+    VisualComponent bad = v;
+    bad.shader_name = "no_such_shader";
+    EXPECT(m.spawn(12, t, &bad, &names) == 2);
+    EXPECT(m.flags(0) == ASTRE_FLAGS(1, 5));          // visible | Opaque | ShadowCaster
+    EXPECT(m.flags(1) == 0 && m.flags(2) == 0);       // no Visual / unresolved name: no proxy (visual_system.cpp:26-30)
+    EXPECT(m.rotation(0)[3] == 1.0f && m.scale(0)[1] == 1.0f);   // defaults (transform_system.cpp:36-49)
+    EXPECT(m.slotCount() == 3 && m.liveCount() == 3 && m.pendingCount() == 3);
+    m.despawn(11);
+    EXPECT(!m.contains(11) && m.liveCount() == 2);
+    EXPECT(m.spawn(13, t, &v, &names, /*parent*/ 10) == 1);      // freed slot is reused
+    EXPECT(m.entityAt(1) == 13);
+    bool threw = false;
+    try { m.spawn(13, t, &v, &names); } catch (const std::invalid_argument &) { threw = true; }
+    EXPECT(threw);
+    threw = false;
+    try { m.spawn(0, t, &v, &names); } catch (const std::invalid_argument &) { threw = true; }
+    EXPECT(threw);
+}
+
+struct World {
+    Names names;
+    EntityMirror mirror;
+    astre_gpu_ctx *ctx;
+    GpuTransformSystem transforms;
+    GpuCameraSystem cameras;
+    GpuVisualSystem visuals;
+    explicit World(uint32_t cap)
+        : mirror(cap), ctx(astre_gpu_create(0, cap, 8, 0)), transforms(mirror, ctx), cameras(mirror, transforms), visuals(mirror, ctx)
+    {
+        if (!ctx) { std::printf("astre_gpu_create failed: %s\n", astre_gpu_last_error(nullptr)); std::exit(2); }
+        astre_gpu_set_mesh_bounds(ctx, 8, kBounds);
+    }
+    ~World() { astre_gpu_destroy(ctx); }
+};
+
+// Oracle result for the mirror's current host state and the frame's views.
+static void oracle_frame(const EntityMirror &m, const Frame &f, std::vector<float> &world, std::vector<uint64_t> &keys,
+                         std::vector<uint32_t> &counts)
+{
+    const uint32_t n = m.slotCount(), F = 1 + (uint32_t)f.light_space_matrices.size();
+    std::vector<uint32_t> mesh(n), shader(n);
+    std::vector<uint8_t> flags(n);
+    for (uint32_t i = 0; i < n; ++i) { mesh[i] = m.mesh(i); shader[i] = m.shader(i); flags[i] = m.flags(i); }
+    std::vector<orc_view> views(F);
+    float clip[16];
+    orc_mat4_mul(f.proj_matrix.data(), f.view_matrix.data(), clip);
+    orc_extract_view(clip, ASTRE_PHASE_OPAQUE, &views[0]);
+    for (uint32_t v = 1; v < F; ++v) orc_extract_view(f.light_space_matrices[v - 1].data(), ASTRE_PHASE_SHADOW_CASTER, &views[v]);
+    orc_bounds b[8];
+    std::memcpy(b, kBounds, sizeof b);
+    world.resize(16 * (size_t)n); keys.resize((size_t)n * F); counts.assign(F, 0);
+    const uint64_t total = orc_frame(n, m.position(0), m.rotation(0), m.scale(0), nullptr, mesh.data(), shader.data(), flags.data(),
+                                     b, 8, 1, 0, F, views.data(), world.data(), keys.data(), keys.size(), counts.data());
+    keys.resize(total);
+}
+
+static void check_against_oracle(World &w, Frame &frame)
+{
+    std::vector<float> o_world; std::vector<uint64_t> o_keys; std::vector<uint32_t> o_counts;
+    oracle_frame(w.mirror, frame, o_world, o_keys, o_counts);
+    EXPECT(frame.draw_lists.size() == o_counts.size());
+    size_t k = 0;
+    bool lists_ok = true, models_ok = true;
+    for (size_t v = 0; v < o_counts.size() && v < frame.draw_lists.size(); ++v) {
+        if (frame.draw_lists[v].size() != o_counts[v]) { lists_ok = false; break; }
+        for (uint32_t i = 0; i < o_counts[v]; ++i, ++k) {
+            const uint32_t slot = (uint32_t)(o_keys[k] & ((1ull << 26) - 1));
+            if (frame.draw_lists[v][i] != w.mirror.entityAt(slot)) lists_ok = false;
+            const auto it = frame.render_proxies.find((size_t)w.mirror.entityAt(slot));
+            if (it == frame.render_proxies.end() || !same_bits(it->second.uModel.data(), &o_world[16 * (size_t)slot], 16)) models_ok = false;
+        }
+    }
+    EXPECT(lists_ok);
+    EXPECT(models_ok);
+}
+
+static void test_level0_like_world()
+{
+    World w(64);
+    // 13 props + a camera, in the spirit of level_0.json (one rotated entity, authored scales)
+    const char *meshes[] = {"cube_prefab", "icosphere2_prefab", "cone_prefab", "cylinder_prefab", "quad_prefab"};
+    for (int i = 0; i < 13; ++i) {
+        TransformComponent t;
+        t.position = Vec3{(float)(i % 5) * 4.0f - 8.0f, (float)(i / 5), -(float)i * 3.0f};
+        t.scale = Vec3{1.0f + 0.25f * i, 1.0f, 2.0f};
+        if (i == 3) t.rotation = Quat{0.0f, 0.38268343f, 0.0f, 0.92387953f};
+        VisualComponent v;
+        v.vertex_buffer_name = meshes[i % 5];
+        v.shader_name = (i % 2) ? "deferred_shader" : "basic_shader";
+        v.visible = (i != 7);
+        w.mirror.spawn(100 + i, t, &v, &w.names);
+    }
+    TransformComponent cam;
+    cam.position = Vec3{0, 5, 15};
+    cam.scale = Vec3{1, 1, 1};
+    w.mirror.spawn(5, cam, nullptr, nullptr);          // level_0.json:118-141: entity 5 is the camera
+    w.cameras.active_camera_entity = 5;
+
+    Frame frame;
+    w.transforms.run(0.1f);
+    // TransformSystem: transform_matrix + forward/up/right of every entity
+    bool mats = true, basis = true;
+    for (uint32_t s = 0; s < w.mirror.slotCount(); ++s) {
+        TransformComponent out;
+        w.transforms.read(w.mirror.entityAt(s), out);
+        float m[16], f[3], u[3], r[3];
+        orc_trs_matrix(w.mirror.position(s), w.mirror.rotation(s), w.mirror.scale(s), m);
+        orc_basis(w.mirror.rotation(s), f, u, r);
+        mats &= same_bits(m, out.transform_matrix.data(), 16);
+        basis &= same_bits(f, &out.forward.x, 3) && same_bits(u, &out.up.x, 3) && same_bits(r, &out.right.x, 3);
+    }
+    EXPECT(mats);
+    EXPECT(basis);
+    // CameraSystem
+    w.cameras.run(0.1f, frame);
+    float view[16], proj[16];
+    const float fwd[3] = {0, 0, -1}, up[3] = {0, 1, 0}, pos[3] = {0, 5, 15};
+    orc_camera_view_proj(pos, fwd, up, 60.0f, 1.7f, 0.1f, 1000.0f, view, proj);
+    EXPECT(same_bits(view, frame.view_matrix.data(), 16));
+    EXPECT(same_bits(proj, frame.proj_matrix.data(), 16));
+    // one directional and one spot shadow caster
+    GPULight sun; sun.position = Vec4{0, 30, 0, 1}; sun.direction = Vec4{-0.3f, -1.0f, -0.2f, 1.0f}; sun.cast_shadows = true; sun.shadow_map_index = 0;
+    GPULight spot; spot.position = Vec4{0, 8, 4, 1}; spot.direction = Vec4{0, -0.5f, -1.0f, 3.0f}; spot.outer_cutoff = 0.85f; spot.cast_shadows = true; spot.shadow_map_index = 1;
+    frame.gpu_lights[1] = sun; frame.gpu_lights[2] = spot;
+    frame.shadow_casters_count = 2;
+    frame.light_space_matrices = calculateLightSpaceMatrices(frame);
+    float ls[16];
+    orc_light_space(&sun.position.x, &sun.direction.x, 1, 0.0f, ls);
+    EXPECT(same_bits(ls, frame.light_space_matrices[0].data(), 16));
+    orc_light_space(&spot.position.x, &spot.direction.x, 3, 0.85f, ls);
+    EXPECT(same_bits(ls, frame.light_space_matrices[1].data(), 16));
+    // VisualSystem
+    w.visuals.run(0.1f, frame);
+    EXPECT(!frame.draw_lists.empty() && !frame.draw_lists[0].empty());
+    EXPECT(frame.render_proxies.count(107) == 0);      // visible == false never reaches a list
+    EXPECT(frame.render_proxies.count(5) == 0);        // the camera has no Visual component
+    check_against_oracle(w, frame);
+
+    // script writes between ticks, a despawn and a spawn into the freed slot
+    w.mirror.setPosition(103, Vec3{2.0f, 1.0f, -4.0f});
+    w.mirror.setRotation(104, Quat{0.5f, 0.5f, 0.5f, 0.5f});
+    w.mirror.setScale(105, Vec3{-1.0f, 2.0f, 0.5f});
+    w.mirror.setVisible(107, true);
+    w.mirror.despawn(101);
+    TransformComponent t; t.position = Vec3{1, 1, -6};
+    VisualComponent v; v.vertex_buffer_name = "dome_prefab"; v.shader_name = "deferred_shader";
+    w.mirror.spawn(200, t, &v, &w.names);
+    EXPECT(w.mirror.pendingCount() > 0);
+    w.transforms.run(0.1f);
+    EXPECT(w.mirror.pendingCount() == 0);
+    w.visuals.run(0.1f, frame);
+    EXPECT(frame.render_proxies.count(101) == 0 && frame.render_proxies.count(200) == 1 && frame.render_proxies.count(107) == 1);
+    check_against_oracle(w, frame);
+}
+
+static void test_random_world(uint32_t n)
+{
+    World w(n);
+    std::mt19937 rng(42);
+    std::uniform_real_distribution<float> P(-60.0f, 60.0f), Q(-1.0f, 1.0f), S(0.25f, 3.0f);
+    const char *meshes[] = {"cube_prefab", "icosphere2_prefab", "cone_prefab", "dome_prefab", "quad_prefab", "ghost_mesh"};
+    for (uint32_t i = 0; i < n; ++i) {
+        TransformComponent t;
+        if (i % 7) t.position = Vec3{P(rng), P(rng) * 0.2f, P(rng) - 50.0f};
+        if (i % 3) { Quat q{Q(rng), Q(rng), Q(rng), Q(rng)}; const float l = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w); t.rotation = Quat{q.x / l, q.y / l, q.z / l, q.w / l}; }
+        if (i % 5) t.scale = Vec3{S(rng), S(rng), S(rng)};
+        VisualComponent v;
+        v.vertex_buffer_name = meshes[i % 6];
+        v.shader_name = (i % 4) ? "deferred_shader" : "basic_shader";
+        v.visible = (i % 11) != 0;
+        w.mirror.spawn(1000 + i, t, (i % 13) ? &v : nullptr, &w.names);
+    }
+    TransformComponent cam; cam.position = Vec3{0, 5, 15};
+    w.mirror.spawn(5, cam, nullptr, nullptr);
+    w.cameras.active_camera_entity = 5;
+    Frame frame;
+    w.transforms.run(0.1f);
+    w.cameras.run(0.1f, frame);
+    GPULight sun; sun.position = Vec4{0, 40, -40, 1}; sun.direction = Vec4{-0.3f, -1.0f, -0.2f, 1.0f}; sun.cast_shadows = true; sun.shadow_map_index = 0;
+    frame.gpu_lights[1] = sun;
+    frame.shadow_casters_count = 1;
+    frame.light_space_matrices = calculateLightSpaceMatrices(frame);
+    w.visuals.run(0.1f, frame);
+    EXPECT(frame.draw_lists[0].size() > n / 50);
+    check_against_oracle(w, frame);
+    for (uint32_t i = 0; i < n; i += 17) w.mirror.setPosition(1000 + i, Vec3{P(rng), 1.0f, P(rng) - 50.0f});
+    for (uint32_t i = 0; i < n; i += 29) w.mirror.despawn(1000 + i);
+    w.transforms.run(0.1f);
+    w.visuals.run(0.1f, frame);
+    check_against_oracle(w, frame);
+}
+
+int main(int argc, char **argv)
+{
+    const bool cpu_only = argc > 1 && std::string(argv[1]) == "--cpu";
+    test_mirror_cpu();
+    if (!cpu_only) {
+        test_level0_like_world();
+        test_random_world(20000);
+    }
+    std::printf("%s: %d checks, %d failures%s\n", g_failures ? "FAILED" : "PASSED", g_checks, g_failures, cpu_only ? " (cpu-only subset)" : "");
+    return g_failures ? 1 : 0;
+}
