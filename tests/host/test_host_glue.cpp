@@ -234,7 +234,7 @@ static void test_level0_like_world()
 
 static void test_random_world(uint32_t n)
 {
-    World w(n);
+    World w(n + 1);
     std::mt19937 rng(42);
     std::uniform_real_distribution<float> P(-60.0f, 60.0f), Q(-1.0f, 1.0f), S(0.25f, 3.0f);
     const char *meshes[] = {"cube_prefab", "icosphere2_prefab", "cone_prefab", "dome_prefab", "quad_prefab", "ghost_mesh"};
