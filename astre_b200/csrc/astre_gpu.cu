@@ -62,11 +62,10 @@ struct astre_gpu_ctx {
     uint32_t cap_counts = 0;
     FrameControl *d_ctl = nullptr;
     SortControl *d_sc = nullptr;
-    uint32_t *d_block_hist = nullptr;
-    uint32_t *d_sort_table = nullptr;     // cooperative sort: [tiles][256] counts/prefixes, then 256 totals, then the barrier word
-    uint64_t sort_table_tiles = 0;
-    int coop_grid = 0;                    // co-resident CTAs of k_sort_coop
-    int sort_mode = 0;                    // 0 auto, 1 cooperative, 2 onesweep (ASTRE_SORT)
+    uint32_t *d_block_hist = nullptr;     // [hist_regions][8][256] per-CTA digit histograms
+    uint32_t hist_regions = 0;
+    uint32_t shader_or = 0;               // OR of every shader id uploaded (live bits of the key's shader field)
+    int sort_items = 8;                   // keys per thread in a sort tile (ASTRE_SORT_ITEMS = 8 | 16)
     unsigned long long *d_lookback = nullptr;
     float4 *d_gather = nullptr;
     uint64_t cap_gather = 0;
@@ -87,7 +86,7 @@ struct astre_gpu_ctx {
 
     // cached read-backs of the last frame
     bool frame_done = false, results_cached = false, results_cached_total_valid = false;
-    uint32_t last_flags = 0;
+    uint32_t last_flags = 0, last_sort_passes = 0;
     std::vector<uint32_t> h_counts;
     std::vector<unsigned long long> h_offsets;
     unsigned long long h_total = 0;
@@ -145,6 +144,7 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     P.keys = c->d_keys[0];
     P.counts = c->d_counts;
     P.ctl = c->d_ctl;
+    P.block_hist = c->d_block_hist;
     P.key_cap = c->max_keys;
     P.n_meshes = c->n_meshes;
     P.views_per_world = cull ? c->views_per_world : 0u;
@@ -154,15 +154,17 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     return P;
 }
 
-__global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts, uint32_t epoch)
+__global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts, uint32_t epoch,
+                              uint32_t *block_hist, uint32_t n_hist_words)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         ctl->key_total = 0; ctl->overflow = 0; ctl->pad = 0;
-        ctl->or_lo = 0; ctl->or_hi = 0; ctl->and_lo = 0xFFFFFFFFu; ctl->and_hi = 0xFFFFFFFFu;
-        sc->result_buf = 0; sc->n_keys = 0; sc->n_passes = 0; sc->epoch = epoch;
+        sc->n_keys = 0; sc->epoch = epoch;
     }
+    if (tid < kSortPasses) sc->skip[tid] = 1;
     for (uint32_t i = tid; i < n_counts; i += nth) counts[i] = 0;
+    for (uint32_t i = tid; i < n_hist_words; i += nth) block_hist[i] = 0;
 }
 
 // Depth of every slot; returns the level count or -1 (bad index / cycle).
@@ -256,8 +258,11 @@ int cache_results(astre_gpu_ctx *ctx)
     CK(cudaStreamSynchronize(s));
     CK(cudaMemcpy(&ctl, ctx->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     uint32_t result_buf = 0;
-    if (ctx->last_flags & ASTRE_FRAME_SORT)
-        CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (ctx->last_sort_passes) {   // the sorted keys are in buffer (number of digit passes that were not skipped) & 1
+        uint32_t skip[kSortPasses];
+        CK(cudaMemcpy(skip, ctx->d_sc->skip, sizeof skip, cudaMemcpyDeviceToHost));
+        for (uint32_t p = 0; p < ctx->last_sort_passes; ++p) result_buf ^= skip[p] ? 0u : 1u;
+    }
     ctx->h_counts.assign(n_counts, 0);
     ctx->h_offsets.assign((size_t)n_counts + 1, 0);
     if (n_counts) {
@@ -355,22 +360,12 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaMemset(ctx->d_ctl, 0, sizeof(FrameControl)));
     CKC(cudaMalloc(&ctx->d_sc, sizeof(SortControl)));
     CKC(cudaMemset(ctx->d_sc, 0, sizeof(SortControl)));
-    CKC(cudaMalloc(&ctx->d_block_hist, (size_t)kHistBlocks * kSortPasses * 256 * sizeof(uint32_t)));
-    const size_t n_sort_tiles = (size_t)((ctx->max_keys + kSortTile - 1) / kSortTile) + 1;
+    const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
     CKC(cudaMalloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
     CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
-    ctx->sort_table_tiles = n_sort_tiles;
-    CKC(cudaMalloc(&ctx->d_sort_table, (n_sort_tiles * 256 + 256 + 32) * sizeof(uint32_t)));
-    {
-        int coop = 0, occ_sort = 0;
-        CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_coop, kSortThreads, 0));
-        ctx->coop_grid = coop ? ctx->sm_count * std::min(occ_sort, 2) : 0;
-        if (const char *m = std::getenv("ASTRE_SORT")) {
-            if (!std::strcmp(m, "coop")) ctx->sort_mode = 1;
-            else if (!std::strcmp(m, "onesweep")) ctx->sort_mode = 2;
-        }
-    }
+    ctx->hist_regions = (uint32_t)ctx->sm_count * 2u;
+    CKC(cudaMalloc(&ctx->d_block_hist, (size_t)ctx->hist_regions * kHistWords * sizeof(uint32_t)));
+    if (const char *m = std::getenv("ASTRE_SORT_ITEMS")) ctx->sort_items = std::atoi(m) == 16 ? 16 : 8;
     CKC(cudaEventCreate(&ctx->ev_begin));
     CKC(cudaEventCreate(&ctx->ev_cull0));
     CKC(cudaEventCreate(&ctx->ev_cull1));
@@ -383,7 +378,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaFuncSetAttribute(k_frame_fused<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
     CKC(cudaFuncSetAttribute(k_frame_fused<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
     CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frame_fused<false, false, true>, kBlockThreads, kFusedSmemBytes));
-    ctx->fused_blocks_per_sm = std::max(occ, 1);
+    ctx->fused_blocks_per_sm = std::min(std::max(occ, 1), 2);   // hist_regions = 2 per SM
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -398,7 +393,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_sort_table };
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist };
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -455,6 +450,11 @@ int astre_gpu_upload_entities(astre_gpu_ctx *ctx, uint32_t first, uint32_t count
     }
     CK(cudaStreamSynchronize(s));   // host buffers may be reused by the caller
     for (uint32_t i = 0; i < count; ++i) ctx->h_parent[first + i] = parent_slot ? parent_slot[i] : ASTRE_NO_PARENT;
+    if (shader_id) {
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < count; ++i) acc |= shader_id[i];
+        ctx->shader_or |= acc & 255u;
+    }
     if (entity_id) {
         if (ctx->h_entity_id.empty()) {
             ctx->h_entity_id.resize(ctx->max_entities);
@@ -620,12 +620,29 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     ctx->epoch = (ctx->epoch + 1) & ((1u << 27) - 1u);
     if (ctx->epoch == 0) {   // tag wrapped: clear stale look-back words once
-        const size_t n_sort_tiles = (size_t)((ctx->max_keys + kSortTile - 1) / kSortTile) + 1;
+        const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
         CK(cudaMemsetAsync(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long), s));
         ctx->epoch = 1;
     }
     CK(cudaEventRecord(ctx->ev_begin, s));
-    k_frame_begin<<<8, 256, 0, s>>>(ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch);
+    // digit plan of the sort from the key fields in use (all other key bits are zero in every key)
+    SortPlan plan;
+    std::memset(&plan, 0, sizeof plan);
+    if (sort) {
+        auto bits_for = [](uint64_t max_value) { uint32_t b = 0; while (b < 32 && (max_value >> b)) ++b; return b; };
+        const uint32_t wb = ctx->world_bits;
+        const uint64_t local_max = (ctx->n_worlds > 1 ? ctx->entities_per_world : n) ? (uint64_t)(ctx->n_worlds > 1 ? ctx->entities_per_world : n) - 1 : 0;
+        unsigned long long live = 0;
+        live |= ((1ull << bits_for(local_max)) - 1ull);
+        live |= ((1ull << 14) - 1ull) << (26 - wb);
+        live |= ((1ull << bits_for(ctx->n_meshes ? ctx->n_meshes - 1 : 0)) - 1ull) << (40 - wb);
+        live |= (unsigned long long)ctx->shader_or << (51 - wb);
+        live |= ((1ull << bits_for(ctx->views_per_world ? ctx->views_per_world - 1 : 0)) - 1ull) << (59 - wb);
+        if (wb) live |= ((1ull << wb) - 1ull) << (64 - wb);
+        plan = make_sort_plan(live);
+    }
+    const uint32_t n_hist_words = sort ? ctx->hist_regions * kHistWords : 0u;
+    k_frame_begin<<<64, 256, 0, s>>>(ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch, ctx->d_block_hist, n_hist_words);
     CK_LAUNCH();
 
     const FrameParams P = params_of(ctx, cull);
@@ -639,14 +656,14 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             const uint32_t tiles = ceil_div((uint64_t)hi - base0, kBlockTile);
             const uint32_t g = std::min(tiles, fused_grid);
             if (!cull) {
-                if (hier) k_frame_fused<true, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
-                else k_frame_fused<false, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                if (hier) k_frame_fused<true, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
+                else k_frame_fused<false, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
             } else if (hier) {
-                if (worlds) k_frame_fused<true, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
-                else k_frame_fused<true, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                if (worlds) k_frame_fused<true, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
+                else k_frame_fused<true, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
             } else {
-                if (worlds) k_frame_fused<false, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
-                else k_frame_fused<false, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, lo, hi);
+                if (worlds) k_frame_fused<false, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
+                else k_frame_fused<false, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
             }
         };
         if (!ctx->has_parents) {
@@ -659,7 +676,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
                     launch_range(L.first, L.first + L.count, l != 0);
                 } else {
                     const uint32_t grid = std::min<uint32_t>(ceil_div(L.count, kBlockThreads), (uint32_t)ctx->sm_count * 8);
-                    k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(P, ctx->d_level_slots + L.list_offset, L.count);
+                    k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(P, plan, ctx->d_level_slots + L.list_offset, L.count);
                 }
                 CK_LAUNCH();
             }
@@ -678,33 +695,19 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         }
     }
 
-    if (sort) {
-        // ASTRE_SORT=coop selects the cooperative single-launch sort (both sorts are correct for any count).
-        // (measured r1: the cooperative sort is not yet faster than onesweep at 0.7M keys, so it is opt-in)
-        bool coop = ctx->sort_mode == 1 && ctx->coop_grid > 0;
-        if (coop) {
-            uint32_t *table = ctx->d_sort_table;
-            uint32_t *totals = table + ctx->sort_table_tiles * 256;
-            uint32_t *barrier = totals + 256;
-            CK(cudaMemsetAsync(barrier, 0, sizeof(uint32_t), s));
-            unsigned long long cap = ctx->max_keys;
-            void *args[] = { &ctx->d_keys[0], &ctx->d_keys[1], &ctx->d_ctl, &cap, &ctx->d_sc, &table, &totals, &barrier };
-            CK(cudaLaunchCooperativeKernel((const void *)k_sort_coop, dim3(ctx->coop_grid), dim3(kSortThreads), args, 0, s));
+    if (sort && plan.n_passes) {
+        const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
+        k_sort_scan<<<plan.n_passes, 256, 0, s>>>(ctx->d_sc, ctx->d_block_hist, ctx->hist_regions, ctx->d_ctl, ctx->max_keys);
+        CK_LAUNCH();
+        for (int p = 0; p < (int)plan.n_passes; ++p) {
+            if (ctx->sort_items == 16)
+                k_sort_pass<16><<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
+            else
+                k_sort_pass<8><<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
             CK_LAUNCH();
-        } else {
-            const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
-            k_sort_plan<<<1, 32, 0, s>>>(ctx->d_ctl, ctx->max_keys, ctx->d_sc);
-            CK_LAUNCH();
-            k_sort_hist<<<kHistBlocks, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_sc, ctx->d_block_hist);
-            CK_LAUNCH();
-            k_sort_scan<<<kSortPasses, 256, 0, s>>>(ctx->d_sc, ctx->d_block_hist, kHistBlocks);
-            CK_LAUNCH();
-            for (int p = 0; p < kSortPasses; ++p) {
-                k_sort_pass<<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, p);
-                CK_LAUNCH();
-            }
         }
     }
+    ctx->last_sort_passes = sort ? plan.n_passes : 0u;
     if (n_counts) {
         k_scan_counts<<<1, 256, 0, s>>>(ctx->d_counts, ctx->d_offsets, n_counts);
         CK_LAUNCH();

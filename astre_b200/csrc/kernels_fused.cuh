@@ -33,13 +33,13 @@ namespace astre {
 constexpr int kInBytesFlat = 11 * kWarpTile * 4;           // 5632: planes px..meta
 constexpr int kInBytesHier = 12 * kWarpTile * 4;           // 6144: + parent
 constexpr int kStageBytes = 32 * 9 * 16;                   // 4608: half-tile staging, later 9 words x 128 entities
-constexpr int kKeyCap = 160;                               // per-warp key buffer (>= 128 + slack)
+constexpr int kKeyCap = 144;                               // per-warp key buffer (>= 128 + slack)
 constexpr int kQueueCap = 80;                              // per-warp task queue (< 32 + kDenseMin entries live)
 constexpr int kDenseMin = 40;                              // survivors per view and warp tile that take the dense path
 constexpr int kWarpSmemBytes = kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2;   // 12192
 constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;                           // 97536
 constexpr uint32_t kSmemMeshes = 64;    // bounds tables up to this size are served from shared memory
-constexpr uint32_t kSmemViews = 16;     // views up to this index can take the task path
+constexpr uint32_t kSmemViews = 12;     // views up to this index can take the task path
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -80,6 +80,8 @@ struct KeySink {
     unsigned long long *kbuf;     // shared, kKeyCap entries
     uint32_t fill;                // warp-uniform
     const FrameParams *P;
+    const SortPlan *plan;
+    uint32_t *s_hist;             // shared, this CTA's digit histograms [n_passes][256]
     int lane;
 
     __device__ __forceinline__ void flush()
@@ -89,19 +91,16 @@ struct KeySink {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&P->ctl->key_total, (unsigned long long)fill);
             base = __shfl_sync(0xffffffffu, base, 0);
-            unsigned long long o = 0ull, a = ~0ull;
+            const uint32_t n_passes = plan->n_passes;
             for (uint32_t i = lane; i < fill; i += 32) {
                 const unsigned long long k = kbuf[i], pos = base + i;
-                o |= k; a &= k;
-                if (pos < P->key_cap) P->keys[pos] = k;
-                else P->ctl->overflow = 1u;
-            }
-            // the sort only looks at key bits that differ: feed the frame-wide OR / AND
-            const uint32_t olo = __reduce_or_sync(0xffffffffu, (uint32_t)o), ohi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
-            const uint32_t alo = __reduce_and_sync(0xffffffffu, (uint32_t)a), ahi = __reduce_and_sync(0xffffffffu, (uint32_t)(a >> 32));
-            if (lane == 0) {
-                atomicOr(&P->ctl->or_lo, olo); atomicOr(&P->ctl->or_hi, ohi);
-                atomicAnd(&P->ctl->and_lo, alo); atomicAnd(&P->ctl->and_hi, ahi);
+                if (pos < P->key_cap) {
+                    P->keys[pos] = k;
+                    for (uint32_t q = 0; q < n_passes; ++q)      // the sort's histograms, for free
+                        atomicAdd(&s_hist[q * 256 + sort_digit(plan->seg[q], k)], 1u);
+                } else {
+                    P->ctl->overflow = 1u;
+                }
             }
         }
         __syncwarp();
@@ -200,13 +199,15 @@ __device__ __forceinline__ WorldBounds load_bounds(const float *sb, int idx)
 
 template <bool HIER, bool WORLDS, bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, 2)
-k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uint32_t first, const uint32_t end)
+k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __grid_constant__ SortPlan plan,
+              const uint32_t first, const uint32_t end)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(16) BoundsDev s_bounds[CULL ? kSmemMeshes : 1];
     __shared__ __align__(16) ViewDev s_views[(CULL && !WORLDS) ? kSmemViews : 1];
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
     __shared__ uint32_t s_counts[32];
+    __shared__ uint32_t s_hist[CULL ? kHistWords : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *s_in = s_dyn + warp * kWarpSmemBytes;
@@ -222,6 +223,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uin
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
+    if (CULL) for (uint32_t i = threadIdx.x; i < plan.n_passes * 256u; i += kBlockThreads) s_hist[i] = 0;
     if (CULL && small_table) {
         for (uint32_t i = threadIdx.x; i < P.n_meshes * 2; i += kBlockThreads)   // 32-byte records, two float4 each
             reinterpret_cast<float4 *>(s_bounds)[i] = __ldg(reinterpret_cast<const float4 *>(P.bounds) + i);
@@ -248,7 +250,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uin
         bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
     };
 
-    KeySink sink{ kbuf, 0u, &P, lane };
+    KeySink sink{ kbuf, 0u, &P, &plan, s_hist, lane };
     uint32_t parity = 0;
     if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x);
 
@@ -392,6 +394,11 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const uin
     __syncthreads();
     if (CULL && !WORLDS && threadIdx.x < F && s_counts[threadIdx.x])
         atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
+    if (CULL) {   // this CTA's region of the partial histograms (launches of one frame are stream-ordered)
+        uint32_t *region = P.block_hist + (size_t)blockIdx.x * kHistWords;
+        for (uint32_t i = threadIdx.x; i < plan.n_passes * 256u; i += kBlockThreads)
+            if (s_hist[i]) region[i] += s_hist[i];
+    }
 }
 
 }  // namespace astre

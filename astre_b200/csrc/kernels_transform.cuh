@@ -67,8 +67,6 @@ struct FrameControl {            // one per context, reset at the start of a fra
     unsigned long long key_total; // keys reserved so far (may exceed capacity)
     uint32_t overflow;
     uint32_t pad;
-    uint32_t or_lo, or_hi;        // OR of all keys emitted
-    uint32_t and_lo, and_hi;      // AND of all keys emitted (starts all-ones)
 };
 
 struct FrameParams {
@@ -79,6 +77,7 @@ struct FrameParams {
     unsigned long long *keys;
     uint32_t *counts;              // [n_worlds*views_per_world]
     FrameControl *ctl;
+    uint32_t *block_hist;          // [regions][8][256] per-CTA digit histograms for the sort
     unsigned long long key_cap;
     uint32_t n_meshes;
     uint32_t views_per_world;      // 0 = no culling
@@ -162,6 +161,25 @@ __device__ __forceinline__ unsigned long long make_key(uint32_t wbits, uint32_t 
     k = (k << 14) | (depth & 16383u);
     k = (k << (26 - wbits)) | (unsigned long long)local;
     return k;
+}
+
+// Digit plan of the key sort (kernels_sort.cuh); the cull kernels histogram the digits as they emit keys.
+constexpr int kSortPasses = 8;
+constexpr int kSortSegs = 4;
+constexpr int kHistWords = kSortPasses * 256;
+struct SortPlan {
+    uint32_t n_passes;
+    uint32_t seg[kSortPasses][kSortSegs];   // digit = OR of ((key >> shift) & mask(width)) << lshift; shift | width<<8 | lshift<<16
+};
+__host__ __device__ __forceinline__ uint32_t sort_digit(const uint32_t (&seg)[kSortSegs], unsigned long long key)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (int s = 0; s < kSortSegs; ++s) {
+        const uint32_t w = (seg[s] >> 8) & 255u;
+        d |= ((uint32_t)(key >> (seg[s] & 255u)) & ((1u << w) - 1u)) << ((seg[s] >> 16) & 255u);
+    }
+    return d;
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
@@ -256,7 +274,7 @@ __device__ __forceinline__ void cull_views(const Views &V, const uint32_t F, con
 // Writes the keys of one lane starting at `pos`; with s_counts != nullptr also
 // bumps the per-view shared counters (one world, sparse case).
 template <int K, class Views>
-__device__ __forceinline__ void emit_keys(const FrameParams &P, const Views &V, uint32_t world,
+__device__ __forceinline__ void emit_keys(const FrameParams &P, const SortPlan &plan, const Views &V, uint32_t world,
                                           const WorldBounds (&wb)[K], const uint32_t (&vis)[K],
                                           const uint32_t (&meta)[K], const uint32_t (&local)[K],
                                           unsigned long long pos, uint32_t *s_counts)
@@ -269,11 +287,14 @@ __device__ __forceinline__ void emit_keys(const FrameParams &P, const Views &V, 
             m &= m - 1;
             const unsigned long long key = make_key(P.world_bits, world, v, (meta[k] >> 11) & 255u, meta[k] & 2047u,
                                                     depth14(wb[k], V.depth(v), V.depth_scale(v)), local[k]);
-            if (pos < P.key_cap) P.keys[pos] = key;
-            else P.ctl->overflow = 1u;
+            if (pos < P.key_cap) {
+                P.keys[pos] = key;
+                for (uint32_t q = 0; q < plan.n_passes; ++q)      // region 0; launches of one frame are stream-ordered
+                    atomicAdd(&P.block_hist[q * 256 + sort_digit(plan.seg[q], key)], 1u);
+            } else {
+                P.ctl->overflow = 1u;
+            }
             ++pos;
-            atomicOr(&P.ctl->or_lo, (uint32_t)key); atomicOr(&P.ctl->or_hi, (uint32_t)(key >> 32));
-            atomicAnd(&P.ctl->and_lo, (uint32_t)key); atomicAnd(&P.ctl->and_hi, (uint32_t)(key >> 32));
             if (s_counts) atomicAdd(&s_counts[v], 1u);
         }
     }
@@ -310,7 +331,7 @@ __device__ __forceinline__ void add_counts(const FrameParams &P, uint32_t world,
 // compaction.  Correct for any slot order; the range kernel is the fast path.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlockThreads)
-k_transform_cull_indexed(const FrameParams P, const uint32_t *__restrict__ slots, const uint32_t n)
+k_transform_cull_indexed(const FrameParams P, const __grid_constant__ SortPlan plan, const uint32_t *__restrict__ slots, const uint32_t n)
 {
     __shared__ float4 s_scratch[kBlockThreads * 4];
     const int lane = threadIdx.x & 31;
@@ -362,7 +383,7 @@ k_transform_cull_indexed(const FrameParams P, const uint32_t *__restrict__ slots
             base = __shfl_sync(0xffffffffu, base, 0);
             for (uint32_t v = 0; v < P.views_per_world; ++v)
                 if ((vis[0] >> v) & 1u) atomicAdd(&P.counts[(size_t)world * P.views_per_world + v], 1u);
-            if (cnt) emit_keys<1>(P, V, world, wb, vis, meta, local, base + (incl - cnt), nullptr);
+            if (cnt) emit_keys<1>(P, plan, V, world, wb, vis, meta, local, base + (incl - cnt), nullptr);
         }
     }
 }
