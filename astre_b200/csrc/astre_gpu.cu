@@ -697,7 +697,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     if (sort && plan.n_passes) {
         const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
-        k_sort_scan<<<plan.n_passes, 256, 0, s>>>(ctx->d_sc, ctx->d_block_hist, ctx->hist_regions, ctx->d_ctl, ctx->max_keys);
+        k_sort_scan<<<plan.n_passes, 1024, 0, s>>>(ctx->d_sc, ctx->d_block_hist, ctx->hist_regions, ctx->d_ctl, ctx->max_keys);
         CK_LAUNCH();
         for (int p = 0; p < (int)plan.n_passes; ++p) {
             if (ctx->sort_items == 16)

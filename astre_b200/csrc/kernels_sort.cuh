@@ -83,38 +83,45 @@ __device__ __forceinline__ uint32_t sort_key_count(const FrameControl *ctl, unsi
 
 // Block p: histogram of digit p = sum of the per-CTA partials the cull kernel left, then the
 // exclusive scan over its 256 bins; a digit on which all keys agree is marked skipped.
-__global__ void __launch_bounds__(256)
+// 1024 threads: four groups of 256 bins, each summing a quarter of the regions, 8 loads in flight.
+__global__ void __launch_bounds__(1024)
 k_sort_scan(SortControl *sc, const uint32_t *__restrict__ block_hist, const uint32_t n_regions,
             const FrameControl *ctl, const unsigned long long cap)
 {
+    __shared__ uint32_t s_part[4][256];
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_full;
     const uint32_t p = blockIdx.x;
     const uint32_t n = sort_key_count(ctl, cap);
-    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    if (d == 0) s_full = 0;
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const int d = threadIdx.x & 255, g = threadIdx.x >> 8;
+    if (threadIdx.x == 0) s_full = 0;
+    uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t *src = block_hist + (size_t)p * 256 + d;
-    uint32_t b = 0;
-    for (; b + 4 <= n_regions; b += 4) {
-        c0 += src[(size_t)(b + 0) * kHistWords]; c1 += src[(size_t)(b + 1) * kHistWords];
-        c2 += src[(size_t)(b + 2) * kHistWords]; c3 += src[(size_t)(b + 3) * kHistWords];
-    }
-    for (; b < n_regions; ++b) c0 += src[(size_t)b * kHistWords];
-    const uint32_t c = c0 + c1 + c2 + c3;
-    const uint32_t incl = warp_incl_scan(c, lane);
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (c == n) s_full = 1;
-    uint32_t off = 0;
+    for (uint32_t b = g; b < n_regions; b += 32) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) if (w < warp) off += s_warp[w];
-    sc->hist[p][d] = off + incl - c;
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t r = b + 4u * j;
+            if (r < n_regions) acc[j] += src[(size_t)r * kHistWords];
+        }
+    }
+    s_part[g][d] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
     __syncthreads();
-    if (d == 0) {
-        sc->skip[p] = (s_full || n < 2) ? 1u : 0u;
-        sc->tile_counter[p] = 0;
-        if (p == 0) sc->n_keys = n;
+    if (g == 0) {
+        const int lane = d & 31, warp = d >> 5;
+        const uint32_t c = (s_part[0][d] + s_part[1][d]) + (s_part[2][d] + s_part[3][d]);
+        const uint32_t incl = warp_incl_scan(c, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        if (c == n) s_full = 1;
+        asm volatile("bar.sync 1, 256;");     // only the first 256 threads
+        uint32_t off = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) if (w < warp) off += s_warp[w];
+        sc->hist[p][d] = off + incl - c;
+        if (d == 0) {
+            sc->skip[p] = (s_full || n < 2) ? 1u : 0u;
+            sc->tile_counter[p] = 0;
+            if (p == 0) sc->n_keys = n;
+        }
     }
 }
 
@@ -203,13 +210,28 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
                 st_relaxed(mine, epoch | kFlagPrefix | run);
             } else {
                 st_relaxed(mine, epoch | kFlagAggregate | run);
+                // Windowed look-back: kWindow predecessors are fetched at once (one L2 round trip),
+                // then consumed nearest-first until a prefix closes the sum or an unpublished word
+                // is met (that one is re-fetched as the head of the next window).
+                constexpr int kWindow = 8;
                 int t = (int)tile - 1;
-                while (true) {
-                    const unsigned long long w = ld_relaxed(lookback + (size_t)t * 256 + d);
-                    if ((w >> 34) != (epoch >> 34) || !(w & (kFlagAggregate | kFlagPrefix))) continue;  // not published yet
-                    excl += (uint32_t)w;
-                    if (w & kFlagPrefix) break;
-                    --t;
+                bool done = false;
+                while (!done) {
+                    unsigned long long w[kWindow];
+#pragma unroll
+                    for (int j = 0; j < kWindow; ++j)
+                        w[j] = (t - j >= 0) ? ld_relaxed(lookback + (size_t)(t - j) * 256 + d) : (epoch | kFlagPrefix);
+                    int used = 0;
+#pragma unroll
+                    for (int j = 0; j < kWindow; ++j) {
+                        if (done || used != j) continue;
+                        const bool ready = (w[j] >> 34) == (epoch >> 34) && (w[j] & (kFlagAggregate | kFlagPrefix));
+                        if (!ready) continue;              // used stays j: the window ends here
+                        excl += (uint32_t)w[j];
+                        used = j + 1;
+                        if (w[j] & kFlagPrefix) done = true;
+                    }
+                    t -= used;
                 }
                 st_relaxed(mine, epoch | kFlagPrefix | (unsigned long long)(excl + run));
             }
