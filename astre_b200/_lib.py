@@ -16,6 +16,10 @@ def library_path():
     return os.path.join(_HERE, "libastre_gpu.so")
 
 
+class DrawRun(C.Structure):
+    _fields_ = [("first", C.c_uint32), ("count", C.c_uint32), ("world_view", C.c_uint32), ("shader_mesh", C.c_uint32)]
+
+
 class MeshBounds(C.Structure):
     _fields_ = [("center", C.c_float * 3), ("extent", C.c_float * 3), ("radius", C.c_float), ("reserved", C.c_uint32)]
 
@@ -55,6 +59,7 @@ SIGNATURES = {
     "astre_gpu_read_keys": (C.c_int, [_P, C.c_uint32, C.c_uint32, _U64, C.c_uint64, _U64]),
     "astre_gpu_read_all_keys": (C.c_int, [_P, _U64, C.c_uint64, _U64]),
     "astre_gpu_read_visible_world": (C.c_int, [_P, C.c_uint64, C.c_uint64, _F]),
+    "astre_gpu_read_runs": (C.c_int, [_P, C.POINTER(DrawRun), C.c_uint32, _U32]),
     "astre_gpu_slot_entity": (C.c_int, [_P, C.c_uint32, _U64]),
     "astre_gpu_device_world": (_P, [_P]),
     "astre_gpu_device_counts": (_P, [_P]),

@@ -69,6 +69,9 @@ struct astre_gpu_ctx {
     unsigned long long *d_lookback = nullptr;
     float4 *d_gather = nullptr;
     uint64_t cap_gather = 0;
+    uint2 *d_heads = nullptr;            // draw-run heads (f2), then one counter word
+    uint32_t cap_heads = 0;
+    uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
     uint32_t epoch = 0;
 
     // staging for uploads
@@ -393,7 +396,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist };
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads };
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -764,14 +767,63 @@ int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream)
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     if (!ctx->d_prev) CK(cudaMalloc(&ctx->d_prev, ctx->tile_words() * sizeof(float)));
     CK(cudaMemcpyAsync(ctx->d_prev, ctx->d_tiles, ctx->tile_words() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ctx->n_prev = ctx->n_entities;
     return ASTRE_OK;
 }
 
 int astre_gpu_interpolate(astre_gpu_ctx *ctx, float alpha, void *stream)
 {
-    (void)alpha; (void)stream;
     if (!ctx) return ASTRE_ERR_INVALID;
-    return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_interpolate is not built yet");
+    if (!ctx->d_prev) return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_interpolate needs a prior astre_gpu_snapshot_trs");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    alpha = alpha < 0.0f ? 0.0f : (alpha > 1.0f ? 1.0f : alpha);       // std::clamp, render.cpp:10 (NaN stays NaN there too)
+    const uint32_t n = ctx->n_entities;
+    if (n) {
+        k_interpolate<<<std::min<uint32_t>(ceil_div(n, 256), (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(
+            ctx->d_prev, ctx->d_tiles, ctx->d_world, n, std::min(ctx->n_prev, n), alpha);
+        CK_LAUNCH();
+    }
+    ctx->last_stream = s;
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, uint32_t *n_out)
+{
+    if (!ctx || !n_out || (cap && !runs)) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;
+    if (!(ctx->last_flags & ASTRE_FRAME_SORT)) return fail(ctx, ASTRE_ERR_STATE, "draw runs need ASTRE_FRAME_SORT");
+    if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
+    const uint32_t n = (uint32_t)ctx->h_total;
+    *n_out = 0;
+    if (!n) return ASTRE_OK;
+    if (!ctx->d_heads) {
+        ctx->cap_heads = (uint32_t)std::min<uint64_t>(ctx->max_keys, 1u << 20);
+        CK(cudaMalloc(&ctx->d_heads, ((size_t)ctx->cap_heads + 1) * sizeof(uint2)));
+    }
+    cudaStream_t s = ctx->last_stream;
+    uint32_t *counter = reinterpret_cast<uint32_t *>(ctx->d_heads + ctx->cap_heads);
+    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), s));
+    const uint32_t class_shift = 40u - ctx->world_bits;   // below it: depth and slot
+    k_run_heads<<<std::min<uint32_t>(ceil_div(n, 256), (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(
+        ctx->d_keys[ctx->h_result_buf], n, class_shift, ctx->d_heads, ctx->cap_heads, counter);
+    CK_LAUNCH();
+    uint32_t n_heads = 0;
+    CK(cudaMemcpyAsync(&n_heads, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_heads > ctx->cap_heads) return fail(ctx, ASTRE_ERR_CAPACITY, "%u draw runs exceed the internal capacity %u", n_heads, ctx->cap_heads);
+    std::vector<uint2> heads(n_heads);
+    CK(cudaMemcpy(heads.data(), ctx->d_heads, (size_t)n_heads * sizeof(uint2), cudaMemcpyDeviceToHost));
+    std::sort(heads.begin(), heads.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+    *n_out = n_heads;
+    for (uint32_t i = 0; i < n_heads && i < cap; ++i) {
+        runs[i].first = heads[i].x;
+        runs[i].count = (i + 1 < n_heads ? heads[i + 1].x : n) - heads[i].x;
+        runs[i].world_view = heads[i].y >> 19;
+        runs[i].shader_mesh = heads[i].y & ((1u << 19) - 1u);
+    }
+    return ASTRE_OK;
 }
 
 int astre_gpu_read_world(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, float *out)

@@ -83,6 +83,68 @@ __global__ void k_basis(const float *__restrict__ tiles, float *__restrict__ fwd
     }
 }
 
+// f1: uModel = translate(mix(pa,pb)) * toMat4(slerp(qa,qb)) * scale(mix(sa,sb))  (Render/src/render.cpp:26-39).
+// a = snapshot tiles, b = current tiles.  glm::slerp (ext/quaternion_common.inl): shortest arc, lerp when
+// cos > 1 - epsilon.  Slots >= n_prev have no counterpart in `a` and get their plain transform.
+__global__ void __launch_bounds__(256)
+k_interpolate(const float *__restrict__ tiles_a, const float *__restrict__ tiles_b, float4 *__restrict__ world,
+              uint32_t n, uint32_t n_prev, float alpha)
+{
+    __shared__ float4 s_scratch[256 * 4];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *b = tiles_b + tile_index(i, 0);
+        float p[3], q[4], sc[3];
+        if (i < n_prev) {
+            const float *a = tiles_a + tile_index(i, 0);
+            p[0] = mixf(a[PX * kWarpTile], b[PX * kWarpTile], alpha);
+            p[1] = mixf(a[PY * kWarpTile], b[PY * kWarpTile], alpha);
+            p[2] = mixf(a[PZ * kWarpTile], b[PZ * kWarpTile], alpha);
+            sc[0] = mixf(a[SX * kWarpTile], b[SX * kWarpTile], alpha);
+            sc[1] = mixf(a[SY * kWarpTile], b[SY * kWarpTile], alpha);
+            sc[2] = mixf(a[SZ * kWarpTile], b[SZ * kWarpTile], alpha);
+            const float ax = a[QX * kWarpTile], ay = a[QY * kWarpTile], az = a[QZ * kWarpTile], aw = a[QW * kWarpTile];
+            float zx = b[QX * kWarpTile], zy = b[QY * kWarpTile], zz = b[QZ * kWarpTile], zw = b[QW * kWarpTile];
+            float c = fadd(fadd(fmul(aw, zw), fmul(ax, zx)), fadd(fmul(ay, zy), fmul(az, zz)));   // compute_dot<qua>
+            if (c < 0.0f) { zx = -zx; zy = -zy; zz = -zz; zw = -zw; c = -c; }
+            if (c > 1.0f - 1.1920928955078125e-7f) {
+                q[3] = mixf(aw, zw, alpha); q[0] = mixf(ax, zx, alpha); q[1] = mixf(ay, zy, alpha); q[2] = mixf(az, zz, alpha);
+            } else {
+                const float ang = acosf(c);
+                const float s0 = sinf(fmul(fsub(1.0f, alpha), ang)), s1 = sinf(fmul(alpha, ang)), sd = sinf(ang);
+                q[3] = __fdiv_rn(fadd(fmul(s0, aw), fmul(s1, zw)), sd);
+                q[0] = __fdiv_rn(fadd(fmul(s0, ax), fmul(s1, zx)), sd);
+                q[1] = __fdiv_rn(fadd(fmul(s0, ay), fmul(s1, zy)), sd);
+                q[2] = __fdiv_rn(fadd(fmul(s0, az), fmul(s1, zz)), sd);
+            }
+        } else {
+            p[0] = b[PX * kWarpTile]; p[1] = b[PY * kWarpTile]; p[2] = b[PZ * kWarpTile];
+            q[0] = b[QX * kWarpTile]; q[1] = b[QY * kWarpTile]; q[2] = b[QZ * kWarpTile]; q[3] = b[QW * kWarpTile];
+            sc[0] = b[SX * kWarpTile]; sc[1] = b[SY * kWarpTile]; sc[2] = b[SZ * kWarpTile];
+        }
+        float m[16];
+        trs_matrix(p[0], p[1], p[2], q[0], q[1], q[2], q[3], sc[0], sc[1], sc[2], m, s_scratch + threadIdx.x * 4);
+        float4 *out = world + (size_t)i * 4;
+        out[0] = make_float4(m[0], m[1], m[2], m[3]);
+        out[1] = make_float4(m[4], m[5], m[6], m[7]);
+        out[2] = make_float4(m[8], m[9], m[10], m[11]);
+        out[3] = make_float4(m[12], m[13], m[14], m[15]);
+    }
+}
+
+// f2: heads of the draw runs of the sorted list: key i starts a run when its class
+// (key >> class_shift = world|view|shader|mesh) differs from key i-1's.  Unordered emission.
+__global__ void k_run_heads(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t class_shift,
+                            uint2 *__restrict__ heads, uint32_t cap, uint32_t *__restrict__ counter)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t cls = (uint32_t)(keys[i] >> class_shift);
+        if (i == 0 || cls != (uint32_t)(keys[i - 1] >> class_shift)) {
+            const uint32_t at = atomicAdd(counter, 1u);
+            if (at < cap) heads[at] = make_uint2(i, cls);
+        }
+    }
+}
+
 // Gather world matrices in draw-list order: out[i] = world[slot(keys[first+i])].
 __global__ void k_gather_world(const unsigned long long *__restrict__ keys, unsigned long long first, unsigned long long n,
                                const float4 *__restrict__ world, float4 *__restrict__ out,

@@ -141,6 +141,30 @@ __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long 
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// The segments of one digit unpacked into registers (warp-uniform).
+struct DigitRegs {
+    uint32_t shift[kSortSegs], mask[kSortSegs], lshift[kSortSegs], n;
+    __device__ __forceinline__ void load(const uint32_t (&seg)[kSortSegs])
+    {
+        n = 0;
+#pragma unroll
+        for (int s = 0; s < kSortSegs; ++s) {
+            const uint32_t w = (seg[s] >> 8) & 255u;
+            shift[s] = seg[s] & 255u; mask[s] = (1u << w) - 1u; lshift[s] = (seg[s] >> 16) & 255u;
+            if (w) n = s + 1;
+        }
+    }
+    __device__ __forceinline__ uint32_t of(unsigned long long key) const
+    {
+        uint32_t d = (uint32_t)(key >> shift[0]) & mask[0];
+        if (n > 1) {
+#pragma unroll
+            for (int s = 1; s < kSortSegs; ++s) d |= ((uint32_t)(key >> shift[s]) & mask[s]) << lshift[s];
+        }
+        return d;
+    }
+};
+
 // One digit: single-pass scatter with decoupled look-back.  ITEMS keys per thread.
 template <int ITEMS>
 __global__ void __launch_bounds__(kSortThreads)
@@ -161,6 +185,8 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
     const unsigned long long epoch = ((unsigned long long)sc->epoch * kSortPasses + pass + 1ull) << 34;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    DigitRegs digit;
+    digit.load(plan.seg[pass]);
 
     while (true) {
         __syncthreads();
@@ -173,7 +199,7 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
         // warp-striped load: item i of lane l is key tile*kTile + warp*ITEMS*32 + i*32 + l
         const uint32_t wbase = tile * kTile + warp * (ITEMS * 32);
         unsigned long long key[ITEMS];
-        uint32_t rank[ITEMS];
+        uint32_t rank[ITEMS], dig_of[ITEMS];
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t idx = wbase + i * 32 + lane;
@@ -184,7 +210,8 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t idx = wbase + i * 32 + lane;
             const bool valid = idx < n;
-            const uint32_t dig = sort_digit(plan.seg[pass], key[i]);
+            const uint32_t dig = digit.of(key[i]);
+            dig_of[i] = dig;
             const uint32_t peers = __match_any_sync(0xffffffffu, valid ? dig : (256u + lane));
             const uint32_t before = s_whist[warp][dig];
             rank[i] = before + __popc(peers & lt_mask);
@@ -244,7 +271,7 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t idx = wbase + i * 32 + lane;
-            if (idx < n) out[s_whist[warp][sort_digit(plan.seg[pass], key[i])] + rank[i]] = key[i];
+            if (idx < n) out[s_whist[warp][dig_of[i]] + rank[i]] = key[i];
         }
     }
 }

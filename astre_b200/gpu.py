@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import AstreError, MeshBounds, load_library
+from ._lib import AstreError, DrawRun, MeshBounds, load_library
 
 FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS = 1, 2, 4, 8
 FRAME_ALL = 7
@@ -194,6 +194,14 @@ class GpuContext:
         out = np.empty((n, 16), np.float32) if out is None else out
         self._check(self._lib.astre_gpu_read_visible_world(self._h, int(first_key), int(n), _ptr(out, C.c_float)))
         return out
+
+    def read_runs(self):
+        """Draw runs of the sorted list: array [n, 4] = first, count, world<<5|view, shader<<11|mesh."""
+        n = C.c_uint32()
+        self._check(self._lib.astre_gpu_read_runs(self._h, None, 0, C.byref(n)))
+        runs = (DrawRun * max(n.value, 1))()
+        self._check(self._lib.astre_gpu_read_runs(self._h, runs, n.value, C.byref(n)))
+        return np.array([[r.first, r.count, r.world_view, r.shader_mesh] for r in runs[:n.value]], np.uint32).reshape(-1, 4)
 
     def slot_entity(self, slot):
         e = C.c_uint64()

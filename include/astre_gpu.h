@@ -177,7 +177,10 @@ ASTRE_API int astre_gpu_last_cull_ms(astre_gpu_ctx *ctx, float *ms);
 
 /* f1: interpolateFrame's per-proxy step (Render/src/render.cpp:26-39): the TRS of
  * the previous tick is kept on the device by astre_gpu_snapshot_trs; this writes
- * translate(mix(p)) * toMat4(slerp(q)) * scale(mix(s)) into the world buffer. */
+ * translate(mix(p)) * toMat4(slerp(q)) * scale(mix(s)) into the world buffer for every
+ * slot that existed at the snapshot (later slots get their plain transform, like a proxy
+ * that is missing from frame `a`, render.cpp:28-29).  alpha is clamped to [0,1] (render.cpp:10).
+ * slerp uses acosf/sinf: results agree with the CPU to a few ULP, not bit for bit. */
 ASTRE_API int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream);
 ASTRE_API int astre_gpu_interpolate(astre_gpu_ctx *ctx, float alpha, void *stream);
 
@@ -201,6 +204,18 @@ ASTRE_API int astre_gpu_read_all_keys(astre_gpu_ctx *ctx, uint64_t *keys, uint64
 /* World matrices of the first n keys of the sorted list, in list order (what
  * VisualSystem copies into RenderProxy.inputs["uModel"], visual_system.cpp:47). */
 ASTRE_API int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_t n, float *mat4_colmajor);
+/* f2: the sorted list of the last frame cut into draw runs -- maximal stretches of keys with the
+ * same (world, view, shader, mesh), i.e. what one instanced / indirect draw covers instead of one
+ * IRenderer::render per proxy (Pipeline/src/deferred_shading.cpp:115-132, Render/src/opengl/opengl.cpp:563-670).
+ * `first` indexes the whole sorted key list (astre_gpu_read_all_keys); runs come back in list order. */
+typedef struct {
+    uint32_t first;
+    uint32_t count;
+    uint32_t world_view;    /* world << 5 | view   */
+    uint32_t shader_mesh;   /* shader << 11 | mesh */
+} astre_draw_run;
+ASTRE_API int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, uint32_t *n_out);
+
 /* Entity id of a slot (the id given at upload). */
 ASTRE_API int astre_gpu_slot_entity(const astre_gpu_ctx *ctx, uint32_t slot, uint64_t *entity_id);
 

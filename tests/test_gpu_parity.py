@@ -224,3 +224,50 @@ def test_repeated_frames_are_identical(oracle):
                 ref = k
             assert np.array_equal(k, ref)
     assert np.array_equal(ref, oracle.frame(s)[1])
+
+
+def test_draw_runs(oracle):
+    """f2: the sorted list cut into (view, shader, mesh) runs, against numpy on the oracle's keys."""
+    s = scenes.config3(300_000)
+    with GpuContext(s.n, max_views=5) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        keys = ctx.read_all_keys()
+        runs = ctx.read_runs()
+    _, o_keys, _ = oracle.frame(s)
+    assert np.array_equal(keys, o_keys)
+    cls = (o_keys >> np.uint64(40)).astype(np.uint64)
+    heads = np.flatnonzero(np.concatenate([[True], cls[1:] != cls[:-1]]))
+    assert np.array_equal(runs[:, 0], heads)
+    assert np.array_equal(runs[:, 1], np.diff(np.concatenate([heads, [len(o_keys)]])))
+    assert np.array_equal(runs[:, 2], (cls[heads] >> np.uint64(19)).astype(np.uint32))
+    assert np.array_equal(runs[:, 3], (cls[heads] & np.uint64((1 << 19) - 1)).astype(np.uint32))
+    assert runs[:, 1].sum() == len(o_keys) and len(runs) <= 5 * 4 * 8
+
+
+def test_interpolate(oracle):
+    """f1: interpolateFrame's per-proxy matrix.  Exact where glm::slerp takes its lerp branch or alpha is 0/1
+    on equal rotations; a few ULP elsewhere (acosf/sinf differ between libm and CUDA)."""
+    a, b = scenes.config1(20_000), scenes.config1(20_000)
+    rng = np.random.default_rng(9)
+    b.pos = (a.pos + rng.normal(size=a.pos.shape).astype(np.float32)).astype(np.float32)
+    b.scale = (a.scale * np.float32(1.25)).astype(np.float32)
+    q = rng.normal(size=a.rot.shape).astype(np.float32)
+    b.rot = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    b.rot[::3] = a.rot[::3]                 # equal rotations -> lerp branch when |q| == 1
+    with GpuContext(a.n) as ctx:
+        scenes.load_into(ctx, a)
+        ctx.frame(gpu.FRAME_TRANSFORM)
+        ctx.snapshot_trs()
+        ctx.update_trs_range(0, a.n, b.pos, b.rot, b.scale)
+        for alpha in (0.0, 0.3, 1.0, 2.5):
+            ctx.interpolate(alpha)
+            got = ctx.read_world(0, a.n)
+            exp = oracle.interpolate(alpha, (a.pos, a.rot, a.scale), (b.pos, b.rot, b.scale))
+            finite = np.isfinite(exp).all(axis=1) & np.isfinite(got).all(axis=1)
+            assert finite.mean() > 0.99
+            assert np.allclose(got[finite], exp[finite], rtol=2e-5, atol=2e-5), alpha
+            # translation column and the last row never touch the trig path: exact
+            assert np.array_equal(oracle_lib.bits(got[:, 12:16]), oracle_lib.bits(exp[:, 12:16]))
+        ctx.frame(gpu.FRAME_TRANSFORM)       # the plain transform of the current TRS is unaffected
+        assert np.array_equal(oracle_lib.bits(ctx.read_world(0, a.n)), oracle_lib.bits(oracle.transform_flat(b.pos, b.rot, b.scale)))
