@@ -75,8 +75,10 @@ struct astre_gpu_ctx {
     uint32_t epoch = 0;
 
     // staging for uploads
-    unsigned char *d_stage = nullptr;
+    unsigned char *d_stage = nullptr;    // two staging halves of stage_entities * 64 bytes
     uint32_t stage_entities = 0;
+    cudaStream_t copy_stream = nullptr;  // H2D copies of chunk i+1 overlap the ingest kernel of chunk i
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_ingested[2] = {nullptr, nullptr};
 
     // hierarchy
     std::vector<uint32_t> h_parent;
@@ -284,8 +286,13 @@ int cache_results(astre_gpu_ctx *ctx)
 int ensure_stage(astre_gpu_ctx *ctx)
 {
     if (ctx->d_stage) return ASTRE_OK;
-    ctx->stage_entities = std::min<uint32_t>(std::max<uint32_t>(ctx->max_entities, 1u), 1u << 20);
-    CK(cudaMalloc(&ctx->d_stage, (size_t)ctx->stage_entities * 64));
+    ctx->stage_entities = std::min<uint32_t>(std::max<uint32_t>(ctx->max_entities, 1u), 1u << 19);
+    CK(cudaMalloc(&ctx->d_stage, (size_t)ctx->stage_entities * 64 * 2));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_ingested[i], cudaEventDisableTiming));
+    }
     return ASTRE_OK;
 }
 
@@ -400,6 +407,11 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     for (void *p : ptrs) if (p) cudaFree(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_ingested[i]) cudaEventDestroy(ctx->ev_ingested[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -475,26 +487,35 @@ static int update_trs_impl(astre_gpu_ctx *ctx, const uint32_t *slots, uint32_t f
 {
     CK(cudaSetDevice(ctx->device));
     if (int rc = ensure_stage(ctx)) return rc;
-    cudaStream_t s = ctx->stream;
-    for (uint32_t done = 0; done < n;) {
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    // Double-buffered: the copies of chunk i+1 (copy stream) run while chunk i is scattered into the
+    // tile records (main stream); a staging half is refilled only after its ingest kernel finished.
+    int chunk = 0;
+    for (uint32_t done = 0; done < n; ++chunk) {
+        const int h = chunk & 1;
         const uint32_t c = std::min(ctx->stage_entities, n - done);
-        unsigned char *st = ctx->d_stage;
+        unsigned char *base = ctx->d_stage + (size_t)h * ctx->stage_entities * 64;
+        unsigned char *st = base;
         float *d_pos = (float *)st;                       st += (size_t)c * 12;
         float *d_scl = (float *)st;                       st += (size_t)c * 12;
-        st = ctx->d_stage + (((size_t)(st - ctx->d_stage) + 15) & ~(size_t)15);
+        st = base + (((size_t)(st - base) + 15) & ~(size_t)15);
         float *d_rot = (float *)st;                       st += (size_t)c * 16;
         uint32_t *d_slots = (uint32_t *)st;
-        if (slots) CK(cudaMemcpyAsync(d_slots, slots + done, (size_t)c * 4, cudaMemcpyHostToDevice, s));
-        if (pos3) CK(cudaMemcpyAsync(d_pos, pos3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
-        if (rot4) CK(cudaMemcpyAsync(d_rot, rot4 + 4 * (size_t)done, (size_t)c * 16, cudaMemcpyHostToDevice, s));
-        if (scl3) CK(cudaMemcpyAsync(d_scl, scl3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, s));
+        if (chunk >= 2) CK(cudaStreamWaitEvent(cs, ctx->ev_ingested[h], 0));
+        if (slots) CK(cudaMemcpyAsync(d_slots, slots + done, (size_t)c * 4, cudaMemcpyHostToDevice, cs));
+        if (pos3) CK(cudaMemcpyAsync(d_pos, pos3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, cs));
+        if (rot4) CK(cudaMemcpyAsync(d_rot, rot4 + 4 * (size_t)done, (size_t)c * 16, cudaMemcpyHostToDevice, cs));
+        if (scl3) CK(cudaMemcpyAsync(d_scl, scl3 + 3 * (size_t)done, (size_t)c * 12, cudaMemcpyHostToDevice, cs));
+        CK(cudaEventRecord(ctx->ev_copied[h], cs));
+        CK(cudaStreamWaitEvent(s, ctx->ev_copied[h], 0));
         const uint32_t grid = std::min<uint32_t>(ceil_div(c, 256), ctx->sm_count * 8);
         k_ingest_trs<<<grid, 256, 0, s>>>(ctx->d_tiles, slots ? d_slots : nullptr, first + done, c, pos3 ? d_pos : nullptr,
                                           rot4 ? d_rot : nullptr, scl3 ? d_scl : nullptr, false);
         CK_LAUNCH();
+        CK(cudaEventRecord(ctx->ev_ingested[h], s));
         done += c;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(cudaStreamSynchronize(s));   // host buffers may be reused by the caller; staging halves are idle again
     return ASTRE_OK;
 }
 

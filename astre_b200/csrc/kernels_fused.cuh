@@ -302,30 +302,36 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
 
         uint32_t qcount = 0;   // warp-uniform
 
-        // One lane-per-task round: the top min(32, qcount) tasks of the queue.
+        // One lane-per-task round: the top min(32, qcount) tasks of the queue.  View records come from
+        // shared memory (one world) or, per task, from the task's world in global memory.
         auto task_round = [&]() {
             const uint32_t n = qcount < 32u ? qcount : 32u;
             const uint32_t qb = qcount - n;
             bool alive = (uint32_t)lane < n;
-            uint32_t v = 0, idx = 0;
+            uint32_t v = 0, idx = 0, tworld = 0;
             if (alive) {
                 const uint32_t t = queue[qb + lane];
                 v = t >> 8;
                 idx = t & 127u;
+                if (WORLDS) tworld = min((wbase + 4u * (idx & 31u) + (idx >> 5)) / P.entities_per_world, P.n_worlds - 1u);
             }
             const WorldBounds w = load_bounds(sb, idx);
-            const ViewDev &sv = s_views[v];
+            const ViewDev *vr = WORLDS ? (P.views + (size_t)tworld * F + v) : &s_views[v];
 #pragma unroll
             for (int p = 0; p < 6; ++p) {
-                const float4 pl = sv.plane[p], ap = sv.aplane[p];
+                const float4 pl = WORLDS ? __ldg(&vr->plane[p]) : vr->plane[p];
+                const float4 ap = WORLDS ? __ldg(&vr->aplane[p]) : vr->aplane[p];
                 alive = alive && !(fadd(plane_dist(w, pl), plane_rad(w, ap)) < 0.0f);
             }
             unsigned long long key = 0;
             if (alive) {
                 const uint32_t mt = __float_as_uint(sb[7 * 128 + idx]);
-                key = make_key(P.world_bits, 0u, v, (mt >> 11) & 255u, mt & 2047u,
-                               depth14(w, sv.depth, sv.depth_scale), __float_as_uint(sb[8 * 128 + idx]));
-                atomicAdd(&s_counts[v], 1u);
+                const float4 dp = WORLDS ? __ldg(&vr->depth) : vr->depth;
+                const float ds = WORLDS ? __ldg(&vr->depth_scale) : vr->depth_scale;
+                key = make_key(P.world_bits, tworld, v, (mt >> 11) & 255u, mt & 2047u, depth14(w, dp, ds),
+                               __float_as_uint(sb[8 * 128 + idx]));
+                if (WORLDS) atomicAdd(&P.counts[(size_t)tworld * F + v], 1u);
+                else atomicAdd(&s_counts[v], 1u);
             }
             sink.append(alive, key);
             qcount = qb;
@@ -350,7 +356,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
             for (int k = 0; k < kPerLane; ++k) { bal[k] = __ballot_sync(0xffffffffu, pass[k]); n_pass += __popc(bal[k]); }
             if (n_pass == 0) continue;
 
-            if (WORLDS || n_pass >= (uint32_t)kDenseMin || v >= kSmemViews) {
+            if (n_pass >= (uint32_t)kDenseMin || (!WORLDS && v >= kSmemViews)) {
                 // dense: four entities per lane, warp-uniform plane loop
                 WorldBounds w4[kPerLane];
 #pragma unroll
@@ -384,9 +390,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
                 while (qcount >= 32u) task_round();
             }
         }
-        if (!WORLDS) {
-            while (qcount) task_round();
-        }
+        while (qcount) task_round();
         __syncwarp();   // the staging buffer is reused by the next tile
     }
 
