@@ -65,7 +65,8 @@ struct astre_gpu_ctx {
     uint32_t *d_block_hist = nullptr;     // [hist_regions][8][256] per-CTA digit histograms
     uint32_t hist_regions = 0;
     uint32_t shader_or = 0;               // OR of every shader id uploaded (live bits of the key's shader field)
-    int sort_items = 8;                   // keys per thread in a sort tile (ASTRE_SORT_ITEMS = 8 | 16)
+    int sort_threads = 256;               // CTA size of k_sort_pass (ASTRE_SORT_THREADS = 256 | 1024), 8 keys per thread
+    int sort_grid = 148;                  // co-resident CTAs of k_sort_pass
     unsigned long long *d_lookback = nullptr;
     float4 *d_gather = nullptr;
     uint64_t cap_gather = 0;
@@ -375,7 +376,13 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
     ctx->hist_regions = (uint32_t)ctx->sm_count * 2u;
     CKC(cudaMalloc(&ctx->d_block_hist, (size_t)ctx->hist_regions * kHistWords * sizeof(uint32_t)));
-    if (const char *m = std::getenv("ASTRE_SORT_ITEMS")) ctx->sort_items = std::atoi(m) == 16 ? 16 : 8;
+    if (const char *m = std::getenv("ASTRE_SORT_THREADS")) ctx->sort_threads = std::atoi(m) == 1024 ? 1024 : 256;
+    {
+        int occ_sort = 0;
+        if (ctx->sort_threads == 256) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_pass<256, 8>, 256, 0));
+        else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_pass<1024, 8>, 1024, 0));
+        ctx->sort_grid = ctx->sm_count * std::max(occ_sort, 1);
+    }
     CKC(cudaEventCreate(&ctx->ev_begin));
     CKC(cudaEventCreate(&ctx->ev_cull0));
     CKC(cudaEventCreate(&ctx->ev_cull1));
@@ -720,14 +727,14 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     }
 
     if (sort && plan.n_passes) {
-        const uint32_t sort_grid = (uint32_t)ctx->sm_count * 4;
+        const uint32_t sort_grid = (uint32_t)ctx->sort_grid;   // co-resident CTAs only (static tile striding)
         k_sort_scan<<<plan.n_passes, 1024, 0, s>>>(ctx->d_sc, ctx->d_block_hist, ctx->hist_regions, ctx->d_ctl, ctx->max_keys);
         CK_LAUNCH();
         for (int p = 0; p < (int)plan.n_passes; ++p) {
-            if (ctx->sort_items == 16)
-                k_sort_pass<16><<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
+            if (ctx->sort_threads == 256)
+                k_sort_pass<256, 8><<<sort_grid, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
             else
-                k_sort_pass<8><<<sort_grid, kSortThreads, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
+                k_sort_pass<1024, 8><<<sort_grid, 1024, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
             CK_LAUNCH();
         }
     }

@@ -165,16 +165,33 @@ struct DigitRegs {
     }
 };
 
-// One digit: single-pass scatter with decoupled look-back.  ITEMS keys per thread.
-template <int ITEMS>
-__global__ void __launch_bounds__(kSortThreads)
+// Lanes of the warp whose 8-bit digit equals this lane's: eight ballots (MATCH.ANY is slower here).
+template <bool BALLOT>
+__device__ __forceinline__ uint32_t match_digit(uint32_t d)
+{
+    if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return m;
+}
+
+// One digit: single-pass scatter with decoupled look-back.  THREADS x ITEMS keys per tile.
+// Measured (tools/sortbench.cu, 46 live bits): 256 x 8 is fastest up to a few million keys
+// (17 us per pass at 0.7M keys, 10 us at 0.1M); 1024 x 8 wins from ~10M keys (fewer look-backs).
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS)
 k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restrict__ buf1,
             SortControl *sc, unsigned long long *__restrict__ lookback, const __grid_constant__ SortPlan plan, const int pass)
 {
-    constexpr int kTile = kSortThreads * ITEMS;
+    constexpr int kTile = THREADS * ITEMS;
+    constexpr int kWarps = THREADS / 32;
     if (sc->skip[pass]) return;
-    __shared__ uint32_t s_whist[kSortWarps][256];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_whist[kWarps][256];
 
     uint32_t executed = 0;                     // passes before this one that moved the keys
     for (int q = 0; q < pass; ++q) executed += sc->skip[q] ? 0u : 1u;
@@ -188,13 +205,13 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
     DigitRegs digit;
     digit.load(plan.seg[pass]);
 
-    while (true) {
+    // Static tile striding: the grid never exceeds the number of co-resident CTAs (the host sizes it from
+    // the occupancy query), so every tile a CTA looks back to is owned by a CTA that is running or done.
+    // (A shared tile counter would serialise ~27 ns per claim on one L2 atomic.)
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(&sc->tile_counter[pass], 1u);
-        for (int i = threadIdx.x; i < kSortWarps * 256; i += blockDim.x) (&s_whist[0][0])[i] = 0;
+        for (int i = threadIdx.x; i < kWarps * 256; i += THREADS) (&s_whist[0][0])[i] = 0;
         __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= n_tiles) return;
 
         // warp-striped load: item i of lane l is key tile*kTile + warp*ITEMS*32 + i*32 + l
         const uint32_t wbase = tile * kTile + warp * (ITEMS * 32);
@@ -205,28 +222,30 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
             const uint32_t idx = wbase + i * 32 + lane;
             key[i] = idx < n ? in[idx] : ~0ull;
         }
-        // stable rank of every key among the keys of its warp with the same digit
+        // stable rank of every key among the keys of its warp with the same digit: the lowest peer lane
+        // bumps the warp's counter (shared atomics of one warp retire in order) and hands the old value out
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const uint32_t idx = wbase + i * 32 + lane;
             const bool valid = idx < n;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
             const uint32_t dig = digit.of(key[i]);
             dig_of[i] = dig;
-            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? dig : (256u + lane));
-            const uint32_t before = s_whist[warp][dig];
+            const uint32_t peers = match_digit<true>(dig) & vmask;
+            const int leader = __ffs(peers) - 1;
+            uint32_t before = 0;
+            if (valid && lane == leader) before = atomicAdd(&s_whist[warp][dig], (uint32_t)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, leader < 0 ? 0 : leader);
             rank[i] = before + __popc(peers & lt_mask);
-            __syncwarp();
-            if (valid && (peers & lt_mask) == 0) s_whist[warp][dig] = before + __popc(peers);
-            __syncwarp();
         }
         __syncthreads();
 
-        // thread d: digit d.  Exclusive prefix over the warps, tile total, look-back.
-        {
+        // thread d < 256: digit d.  Exclusive prefix over the warps, tile total, look-back.
+        if (threadIdx.x < 256) {
             const int d = threadIdx.x;
             uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
+#pragma unroll 8
+            for (int w = 0; w < kWarps; ++w) {
                 const uint32_t c = s_whist[w][d];
                 s_whist[w][d] = run;
                 run += c;
@@ -263,8 +282,8 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
                 st_relaxed(mine, epoch | kFlagPrefix | (unsigned long long)(excl + run));
             }
             const uint32_t base = sc->hist[pass][d] + excl;
-#pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) s_whist[w][d] += base;
+#pragma unroll 8
+            for (int w = 0; w < kWarps; ++w) s_whist[w][d] += base;
         }
         __syncthreads();
 
