@@ -102,6 +102,7 @@ struct astre_gpu_ctx {
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     int fused_blocks_per_sm = 2;
+    bool coop_launch = false;        // device supports cooperative launches (multi-level hierarchy launches)
     ViewSet h_viewset;               // single-world view records, passed as a kernel parameter
     std::string err;
 
@@ -165,7 +166,7 @@ __global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *coun
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
-        ctl->key_total = 0; ctl->overflow = 0; ctl->pad = 0;
+        ctl->key_total = 0; ctl->overflow = 0; ctl->barrier = 0;
         sc->n_keys = 0; sc->epoch = epoch;
     }
     if (tid < kSortPasses) sc->skip[tid] = 1;
@@ -394,8 +395,21 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     CKC(cudaFuncSetAttribute(k_frame_fused<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
     CKC(cudaFuncSetAttribute(k_frame_fused<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
     CKC(cudaFuncSetAttribute(k_frame_fused<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
-    CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_frame_fused<false, false, true>, kBlockThreads, kFusedSmemBytes));
-    ctx->fused_blocks_per_sm = std::min(std::max(occ, 1), 2);   // hist_regions = 2 per SM
+    {
+        // the persistent grid must be co-resident for every instantiation (grid barrier of multi-level launches)
+        const void *variants[] = { (const void *)k_frame_fused<false, false, true>, (const void *)k_frame_fused<false, true, true>,
+                                   (const void *)k_frame_fused<true, false, true>, (const void *)k_frame_fused<true, true, true>,
+                                   (const void *)k_frame_fused<false, false, false>, (const void *)k_frame_fused<true, false, false> };
+        int min_occ = 2;                                            // hist_regions = 2 per SM
+        for (const void *fn : variants) {
+            CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlockThreads, kFusedSmemBytes));
+            min_occ = std::min(min_occ, std::max(occ, 1));
+        }
+        ctx->fused_blocks_per_sm = min_occ;
+        int coop = 0;
+        CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        ctx->coop_launch = coop != 0 && !std::getenv("ASTRE_NO_COOP");
+    }
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -681,34 +695,55 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     if (n) {
         const bool worlds = ctx->n_worlds > 1;
         const uint32_t fused_grid = (uint32_t)(ctx->sm_count * ctx->fused_blocks_per_sm);
-        // one launch over the slot range [lo, hi); hier = world[parent] * local
-        auto launch_range = [&](uint32_t lo, uint32_t hi, bool hier) {
-            const uint32_t base0 = lo & ~(uint32_t)(kWarpTile - 1);
-            const uint32_t tiles = ceil_div((uint64_t)hi - base0, kBlockTile);
-            const uint32_t g = std::min(tiles, fused_grid);
-            if (!cull) {
-                if (hier) k_frame_fused<true, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
-                else k_frame_fused<false, false, false><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
-            } else if (hier) {
-                if (worlds) k_frame_fused<true, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
-                else k_frame_fused<true, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
-            } else {
-                if (worlds) k_frame_fused<false, true, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
-                else k_frame_fused<false, false, true><<<g, kBlockThreads, kFusedSmemBytes, s>>>(P, ctx->h_viewset, plan, lo, hi);
+        // one launch over a list of slot ranges; hier = world[parent] * local (ranges after the first wait for
+        // the previous one through a grid barrier, hence the cooperative launch)
+        uint32_t barrier_rounds = 0;
+        cudaError_t launch_err = cudaSuccess;
+        auto launch_ranges = [&](const LevelTable &LT, bool hier) {
+            uint32_t tiles = 0;
+            for (uint32_t l = 0; l < LT.n; ++l) {
+                const uint32_t base0 = LT.first[l] & ~(uint32_t)(kWarpTile - 1);
+                tiles = std::max(tiles, ceil_div((uint64_t)LT.end[l] - base0, kBlockTile));
             }
+            const uint32_t g = LT.n > 1 ? fused_grid : std::min(tiles, fused_grid);
+            const void *fn;
+            if (!cull) fn = hier ? (const void *)k_frame_fused<true, false, false> : (const void *)k_frame_fused<false, false, false>;
+            else if (hier) fn = worlds ? (const void *)k_frame_fused<true, true, true> : (const void *)k_frame_fused<true, false, true>;
+            else fn = worlds ? (const void *)k_frame_fused<false, true, true> : (const void *)k_frame_fused<false, false, true>;
+            void *args[] = { (void *)&P, (void *)&ctx->h_viewset, (void *)&plan, (void *)&LT };
+            if (LT.n > 1) launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
+            else launch_err = cudaLaunchKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
+            barrier_rounds += (LT.n - 1) * g;
         };
         if (!ctx->has_parents) {
-            launch_range(0u, n, false);
+            LevelTable LT{};
+            LT.n = 1; LT.first[0] = 0; LT.end[0] = n;
+            launch_ranges(LT, false);
+            if (launch_err != cudaSuccess) return fail(ctx, ASTRE_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(launch_err));
             CK_LAUNCH();
         } else {
-            for (size_t l = 0; l < ctx->levels.size(); ++l) {
-                const Level &L = ctx->levels[l];
-                if (L.contiguous) {
-                    launch_range(L.first, L.first + L.count, l != 0);
-                } else {
+            // runs of contiguous levels go into one cooperative launch each; a level whose slots are not a
+            // contiguous range takes the indexed kernel
+            size_t l = 0;
+            while (l < ctx->levels.size()) {
+                if (!ctx->levels[l].contiguous) {
+                    const Level &L = ctx->levels[l];
                     const uint32_t grid = std::min<uint32_t>(ceil_div(L.count, kBlockThreads), (uint32_t)ctx->sm_count * 8);
                     k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(P, plan, ctx->d_level_slots + L.list_offset, L.count);
+                    CK_LAUNCH();
+                    ++l;
+                    continue;
                 }
+                LevelTable LT{};
+                LT.barrier_base = barrier_rounds;
+                while (l < ctx->levels.size() && ctx->levels[l].contiguous && LT.n < (uint32_t)kMaxLevelsPerLaunch &&
+                       (ctx->coop_launch || LT.n == 0)) {
+                    LT.first[LT.n] = ctx->levels[l].first;
+                    LT.end[LT.n] = ctx->levels[l].first + ctx->levels[l].count;
+                    ++LT.n; ++l;
+                }
+                launch_ranges(LT, true);
+                if (launch_err != cudaSuccess) return fail(ctx, ASTRE_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(launch_err));
                 CK_LAUNCH();
             }
         }

@@ -69,6 +69,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// Slot ranges one launch walks in order.  A flat frame has one range; a hierarchy whose levels are
+// contiguous slot ranges passes them all and the kernel (cooperative launch, every CTA resident)
+// separates them with a grid-wide barrier instead of one launch per level.
+constexpr int kMaxLevelsPerLaunch = 32;
+struct LevelTable {
+    uint32_t n;
+    uint32_t barrier_base;                       // barrier arrivals already counted in this frame
+    uint32_t first[kMaxLevelsPerLaunch], end[kMaxLevelsPerLaunch];
+};
+
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // The registers one lane holds of its warp tile: four entities per component.
 struct LaneInputs {
     float4 px, py, pz, qx, qy, qz, qw, sx, sy, sz;
@@ -144,8 +169,10 @@ __device__ __forceinline__ void transform_tile(const FrameParams &P, const LaneI
         if (HIER) {
             const uint32_t par = u4get(in.parent, k);
             if (active && par != kNoParent) {
+                // L2 loads: the parent row was written by another SM (previous level of the same launch, or
+                // an earlier launch) and may share a 128-byte line with a matrix this SM read before it existed
                 const float4 *pw = P.world + (size_t)par * 4;
-                const float4 a0 = pw[0], a1 = pw[1], a2 = pw[2], a3 = pw[3];
+                const float4 a0 = __ldcg(pw), a1 = __ldcg(pw + 1), a2 = __ldcg(pw + 2), a3 = __ldcg(pw + 3);
                 const float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
                                      a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
                 float w[16];
@@ -200,7 +227,7 @@ __device__ __forceinline__ WorldBounds load_bounds(const float *sb, int idx)
 template <bool HIER, bool WORLDS, bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, 2)
 k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __grid_constant__ SortPlan plan,
-              const uint32_t first, const uint32_t end)
+              const __grid_constant__ LevelTable LT)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(16) BoundsDev s_bounds[CULL ? kSmemMeshes : 1];
@@ -239,6 +266,11 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     }
     __syncthreads();
 
+    KeySink sink{ kbuf, 0u, &P, &plan, s_hist, lane };
+    uint32_t parity = 0;
+
+    for (uint32_t level = 0; level < LT.n; ++level) {
+    const uint32_t first = LT.first[level], end = LT.end[level];
     const uint32_t base0 = first & ~(uint32_t)(kWarpTile - 1);
     const uint32_t n_tiles = (end - base0 + kBlockTile - 1) / kBlockTile;
 
@@ -249,9 +281,6 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
         mbar_expect_tx(bar, kInBytes);
         bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
     };
-
-    KeySink sink{ kbuf, 0u, &P, &plan, s_hist, lane };
-    uint32_t parity = 0;
     if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x);
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -392,6 +421,9 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
         }
         while (qcount) task_round();
         __syncwarp();   // the staging buffer is reused by the next tile
+    }
+    // next level reads the matrices this one wrote: every CTA of the (cooperative) grid meets here
+    if (level + 1 < LT.n) grid_barrier(&P.ctl->barrier, LT.barrier_base + (level + 1) * gridDim.x);
     }
 
     if (CULL) sink.flush();

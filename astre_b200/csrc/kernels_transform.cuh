@@ -66,7 +66,7 @@ struct BoundsDev {   // 32 B; extents and radius are >= 0 (checked by astre_gpu_
 struct FrameControl {            // one per context, reset at the start of a frame
     unsigned long long key_total; // keys reserved so far (may exceed capacity)
     uint32_t overflow;
-    uint32_t pad;
+    uint32_t barrier;             // arrivals at the grid barrier of multi-level launches
 };
 
 struct FrameParams {

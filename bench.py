@@ -130,6 +130,30 @@ def cpu_port_frame(scene_arrays, n, threads=None):
     return dt, int(total), o.lib.orc_max_threads()
 
 
+def cpu_reference_layout(scene, n):
+    """B0 of SURVEY.md 8d: TransformSystem::run + VisualSystem::run over the reference's storage shape (hash map of
+    per-entity structs, one thread -- oracle/ref_store.cpp).  Returns entities/s."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    so = os.path.join(oracle_lib.ORACLE_DIR, "_build", "libastre_refstore.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", oracle_lib.ORACLE_DIR], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.refstore_create.restype = C.c_void_p
+    lib.refstore_visual.restype = C.c_uint64
+    p = oracle_lib._p
+    st = lib.refstore_create(C.c_uint32(n), p(scene.pos, C.c_float), p(scene.rot, C.c_float), p(scene.scale, C.c_float),
+                             p(scene.mesh, C.c_uint32), p(scene.shader, C.c_uint32), p(scene.flags, C.c_uint8))
+    try:
+        t0 = time.perf_counter()
+        lib.refstore_transform(C.c_void_p(st))
+        lib.refstore_visual(C.c_void_p(st))
+        return n / (time.perf_counter() - t0)
+    finally:
+        lib.refstore_destroy(C.c_void_p(st))
+
+
 def scene_arrays(scene, n):
     return (scene.pos[:n], scene.rot[:n], scene.scale[:n], scene.mesh[:n], scene.shader[:n], scene.flags[:n],
             scene.bounds, scene.clip, scene.masks)
@@ -315,7 +339,10 @@ def main():
             dts.append(dt)
         cpu = {"value": n / float(np.mean(dts)), "unit": "entities/s", "cores": threads, "kind": "port",
                "sample": f"{reps} full frames of the same {n}-entity workload (oracle/astre_oracle.c, OpenMP, all host cores)",
-               "keys_match_gpu": bool(tot == total_keys)}
+               "keys_match_gpu": bool(tot == total_keys),
+               "reference_layout_1thread": {"value": cpu_reference_layout(scene, 1_048_576), "unit": "entities/s",
+                                            "what": "transform + proxy emission over a hash map of per-entity structs, 1 thread, "
+                                                    "first 1,048,576 entities (oracle/ref_store.cpp; no culling, no sort)"}}
 
     if rank == 0:
         line = {

@@ -174,3 +174,47 @@ def test_interpolate_endpoints(oracle):
     assert np.array_equal(oracle_lib.bits(oracle.interpolate(7.5, A, B)), oracle_lib.bits(w1))
     half = oracle.interpolate(0.5, A, B)
     assert np.allclose(half[unit][:, 12:15], (a.pos[unit] + b.pos[unit]) / 2, rtol=1e-6, atol=1e-5)
+
+
+def test_view_box_contains_the_view_volume(oracle):
+    """Spec step 1 operand: the world-space box of a view.  ortho(-2,2,-1,1,1,3) with an identity view is the box
+    x[-2,2] y[-1,1] z[-3,-1]; the box is widened by 1e-4 of its size + 1e-6 and rounded outwards."""
+    clip = np.array([0.5, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, -2, 1], np.float32).reshape(1, 1, 16)
+    v = oracle.make_views(clip, [1])[0]
+    lo, hi = np.array(list(v.lo)[:3]), np.array(list(v.hi)[:3])
+    assert np.all(lo <= [-2, -1, -3]) and np.all(lo >= np.array([-2, -1, -3]) - 1e-3)
+    assert np.all(hi >= [2, 1, -1]) and np.all(hi <= np.array([2, 1, -1]) + 1e-3)
+    nlo, nhi = npr.view_box(clip[0, 0])
+    assert np.array_equal(nlo, lo.astype(np.float32)) and np.array_equal(nhi, hi.astype(np.float32))
+    # a singular clip matrix disables the box test instead of culling everything
+    v = oracle.make_views(np.zeros((1, 1, 16), np.float32), [1])[0]
+    assert list(v.lo)[:3] == [-np.inf] * 3 and list(v.hi)[:3] == [np.inf] * 3
+    # the level_0 camera: far corners reach +-1000*tan(30deg)*1.7 in x
+    c = scenes.camera_clip()
+    lo, hi = npr.view_box(c)
+    assert 980 < hi[0] < 983 and -983 < lo[0] < -980 and -986 < lo[2] < -984 and 14.9 < hi[2] < 15.1
+
+
+def test_reference_layout_baseline_matches_oracle(oracle):
+    """B0 (oracle/ref_store.cpp): the oracle arithmetic over a hash map of per-entity structs gives the same matrices."""
+    import ctypes as C
+    import subprocess
+    so = os.path.join(oracle_lib.ORACLE_DIR, "_build", "libastre_refstore.so")
+    subprocess.run(["make", "-C", oracle_lib.ORACLE_DIR], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.refstore_create.restype = C.c_void_p
+    lib.refstore_visual.restype = C.c_uint64
+    s = scenes.config1(5000)
+    p = oracle_lib._p
+    st = lib.refstore_create(C.c_uint32(s.n), p(s.pos, C.c_float), p(s.rot, C.c_float), p(s.scale, C.c_float),
+                             p(s.mesh, C.c_uint32), p(s.shader, C.c_uint32), p(s.flags, C.c_uint8))
+    try:
+        lib.refstore_transform(C.c_void_p(st))
+        assert lib.refstore_visual(C.c_void_p(st)) == s.n
+        ref = oracle.transform_flat(s.pos, s.rot, s.scale)
+        m = np.empty(16, np.float32)
+        for i in (0, 1, 63, 1023, 4999):
+            lib.refstore_read_world(C.c_void_p(st), C.c_uint32(i), p(m, C.c_float))
+            assert np.array_equal(oracle_lib.bits(m), oracle_lib.bits(ref[i]))
+    finally:
+        lib.refstore_destroy(C.c_void_p(st))
