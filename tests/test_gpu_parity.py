@@ -271,3 +271,31 @@ def test_interpolate(oracle):
             assert np.array_equal(oracle_lib.bits(got[:, 12:16]), oracle_lib.bits(exp[:, 12:16]))
         ctx.frame(gpu.FRAME_TRANSFORM)       # the plain transform of the current TRS is unaffected
         assert np.array_equal(oracle_lib.bits(ctx.read_world(0, a.n)), oracle_lib.bits(oracle.transform_flat(b.pos, b.rot, b.scale)))
+
+
+def test_stress_moving_camera_and_dirty_sets(oracle):
+    """Many frames on one context: the camera turns, entities move, flags flip -- every frame equals the oracle
+    (shakes out stale state between frames: look-back epochs, histograms, counters, key buffers)."""
+    s = scenes.config3(120_000)
+    s.pos = (s.pos * np.float32(0.1)).astype(np.float32)
+    rng = np.random.default_rng(21)
+    with GpuContext(s.n, max_views=5) as ctx:
+        scenes.load_into(ctx, s)
+        for it in range(24):
+            clips = [scenes.camera_clip(yaw_deg=15.0 * it)] + scenes.cascade_clips()
+            s.clip = np.stack(clips)[None].astype(np.float32)
+            ctx.set_views(s.clip[0], s.masks)
+            slots = rng.choice(s.n, 3000, replace=False).astype(np.uint32)
+            s.pos[slots] += rng.normal(scale=5.0, size=(3000, 3)).astype(np.float32)
+            ctx.update_trs(slots, pos=s.pos[slots])
+            fl = rng.choice(s.n, 500, replace=False).astype(np.uint32)
+            s.flags[fl] ^= 1
+            ctx.update_flags(fl, s.flags[fl])
+            ctx.frame()
+            keys, counts = ctx.read_all_keys(), ctx.read_counts()
+            if it % 4 == 3 or it < 2:
+                _, o_keys, o_counts = oracle.frame(s)
+                assert np.array_equal(counts, o_counts), it
+                assert np.array_equal(keys, o_keys), it
+            else:
+                assert np.all(keys[1:] > keys[:-1]) and counts.sum() == len(keys)
