@@ -159,6 +159,7 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     P.n_worlds = c->n_worlds;
     P.entities_per_world = c->n_worlds > 1 ? c->entities_per_world : 0u;
     P.world_bits = c->world_bits;
+    P.world_cache = (c->n_worlds > 1 && c->entities_per_world % kWarpTile == 0 && c->views_per_world <= (uint32_t)kWorldCacheViews) ? 1u : 0u;
     return P;
 }
 

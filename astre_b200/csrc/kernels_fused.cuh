@@ -36,8 +36,9 @@ constexpr int kStageBytes = 32 * 9 * 16;                   // 4608: half-tile st
 constexpr int kKeyCap = 144;                               // per-warp key buffer (>= 128 + slack)
 constexpr int kQueueCap = 80;                              // per-warp task queue (< 32 + kDenseMin entries live)
 constexpr int kDenseMin = 40;                              // survivors per view and warp tile that take the dense path
-constexpr int kWarpSmemBytes = kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2;   // 12192
-constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;                           // 97536
+constexpr int kWorldCacheViews = 1;                        // batched worlds: view records of the warp's world, fetched with the tile
+constexpr int kWarpSmemBytes = kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2 + 2 * kWorldCacheViews * 256;   // 12576 (cache is double-buffered)
+constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;                           // 100608
 constexpr uint32_t kSmemMeshes = 64;    // bounds tables up to this size are served from shared memory
 constexpr uint32_t kSmemViews = 12;     // views up to this index can take the task path
 
@@ -93,6 +94,19 @@ __device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t target)
     }
     __syncthreads();
 }
+
+// View records in shared memory (the warp's world, batched worlds).
+struct SmemViews {
+    const ViewDev *v;
+    __device__ __forceinline__ float4 plane(uint32_t i, int p) const { return v[i].plane[p]; }
+    __device__ __forceinline__ float4 aplane(uint32_t i, int p) const { return v[i].aplane[p]; }
+    __device__ __forceinline__ float4 depth(uint32_t i) const { return v[i].depth; }
+    __device__ __forceinline__ float depth_scale(uint32_t i) const { return v[i].depth_scale; }
+    __device__ __forceinline__ uint32_t mask(uint32_t i) const { return v[i].phase_mask; }
+    __device__ __forceinline__ uint32_t sym(uint32_t i) const { return v[i].sym; }
+    __device__ __forceinline__ float4 lo(uint32_t i) const { return v[i].lo; }
+    __device__ __forceinline__ float4 hi(uint32_t i) const { return v[i].hi; }
+};
 
 // The registers one lane holds of its warp tile: four entities per component.
 struct LaneInputs {
@@ -242,6 +256,10 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     float *sb = reinterpret_cast<float *>(stage);
     unsigned long long *kbuf = reinterpret_cast<unsigned long long *>(s_in + kInBytesHier + kStageBytes);
     unsigned short *queue = reinterpret_cast<unsigned short *>(s_in + kInBytesHier + kStageBytes + kKeyCap * 8);
+    const ViewDev *vcache2 = reinterpret_cast<const ViewDev *>(s_in + kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2);
+    // Batched worlds whose size is a multiple of the warp tile: all 128 entities of a warp tile share one world,
+    // so its view records ride along with the tile record (same mbarrier) instead of being read from L2 per plane.
+    const bool wcache = WORLDS && P.world_cache != 0;
     const uint32_t bar = smem_u32(&s_bar[warp]);
     const uint32_t s_in_addr = smem_u32(s_in);
     const uint32_t F = P.views_per_world;
@@ -274,14 +292,21 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     const uint32_t base0 = first & ~(uint32_t)(kWarpTile - 1);
     const uint32_t n_tiles = (end - base0 + kBlockTile - 1) / kBlockTile;
 
-    // lane 0: one bulk copy of the warp tile's record
-    auto issue = [&](uint32_t tile) {
+    // lane 0: one bulk copy of the warp tile's record (+ its world's view records into cache half `half`)
+    auto issue = [&](uint32_t tile, uint32_t half) {
         const uint32_t wb0 = base0 + tile * kBlockTile + warp * kWarpTile;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, kInBytes);
-        bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
+        if (wcache) {
+            const uint32_t w = min(wb0 / P.entities_per_world, P.n_worlds - 1u);
+            mbar_expect_tx(bar, kInBytes + F * 256u);
+            bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
+            bulk_g2s(smem_u32(vcache2 + half * kWorldCacheViews), P.views + (size_t)w * F, F * 256u, bar);
+        } else {
+            mbar_expect_tx(bar, kInBytes);
+            bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
+        }
     };
-    if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x);
+    if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x, parity);
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t tbase = base0 + tile * kBlockTile;
@@ -289,6 +314,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
         const bool full = tbase >= first && tbase + kBlockTile <= end;   // block-uniform
 
         mbar_wait(bar, parity);
+        const ViewDev *vcache = vcache2 + parity * kWorldCacheViews;    // this tile's world (batched worlds)
         parity ^= 1u;
         LaneInputs in;
         {
@@ -303,7 +329,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
         __syncwarp();   // every lane holds its inputs: the buffer may be refilled
         {
             const uint32_t next = tile + gridDim.x;
-            if (next < n_tiles && lane == 0) issue(next);
+            if (next < n_tiles && lane == 0) issue(next, parity);
         }
 
         WorldBounds wb[kPerLane];
@@ -345,31 +371,40 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
                 if (WORLDS) tworld = min((wbase + 4u * (idx & 31u) + (idx >> 5)) / P.entities_per_world, P.n_worlds - 1u);
             }
             const WorldBounds w = load_bounds(sb, idx);
-            const ViewDev *vr = WORLDS ? (P.views + (size_t)tworld * F + v) : &s_views[v];
+            const bool from_global = WORLDS && !wcache;
+            const ViewDev *vr = WORLDS ? (wcache ? &vcache[v] : P.views + (size_t)tworld * F + v) : &s_views[v];
 #pragma unroll
             for (int p = 0; p < 6; ++p) {
-                const float4 pl = WORLDS ? __ldg(&vr->plane[p]) : vr->plane[p];
-                const float4 ap = WORLDS ? __ldg(&vr->aplane[p]) : vr->aplane[p];
+                const float4 pl = from_global ? __ldg(&vr->plane[p]) : vr->plane[p];
+                const float4 ap = from_global ? __ldg(&vr->aplane[p]) : vr->aplane[p];
                 alive = alive && !(fadd(plane_dist(w, pl), plane_rad(w, ap)) < 0.0f);
             }
             unsigned long long key = 0;
             if (alive) {
                 const uint32_t mt = __float_as_uint(sb[7 * 128 + idx]);
-                const float4 dp = WORLDS ? __ldg(&vr->depth) : vr->depth;
-                const float ds = WORLDS ? __ldg(&vr->depth_scale) : vr->depth_scale;
+                const float4 dp = from_global ? __ldg(&vr->depth) : vr->depth;
+                const float ds = from_global ? __ldg(&vr->depth_scale) : vr->depth_scale;
                 key = make_key(P.world_bits, tworld, v, (mt >> 11) & 255u, mt & 2047u, depth14(w, dp, ds),
                                __float_as_uint(sb[8 * 128 + idx]));
-                if (WORLDS) atomicAdd(&P.counts[(size_t)tworld * F + v], 1u);
+                if (WORLDS) { if (!wcache) atomicAdd(&P.counts[(size_t)tworld * F + v], 1u); }
                 else atomicAdd(&s_counts[v], 1u);
             }
-            sink.append(alive, key);
+            const uint32_t c = sink.append(alive, key);
+            // one world per warp tile and a single cached view: one global atomic per round, not per key
+            // (per-key REDs on a few thousand counters saturate the L2 atomic units and stall every load)
+            if (WORLDS && wcache && lane == 0 && c) atomicAdd(&P.counts[(size_t)world * F], c);
             qcount = qb;
         };
 
         for (uint32_t v = 0; v < F; ++v) {
             bool pass[kPerLane];
             uint32_t bal[kPerLane], n_pass = 0;
-            if (WORLDS) {
+            if (WORLDS && wcache) {
+                const uint32_t mask = vcache[v].phase_mask;
+                const float4 lo = vcache[v].lo, hi = vcache[v].hi;
+#pragma unroll
+                for (int k = 0; k < kPerLane; ++k) pass[k] = (phases[k] & mask) != 0 && box_overlaps(box[k], lo, hi);
+            } else if (WORLDS) {
                 const GlobalViews GV{ P.views + (size_t)world * F };
                 const uint32_t mask = GV.mask(v);
                 const float4 lo = GV.lo(v), hi = GV.hi(v);
@@ -392,19 +427,26 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
                 for (int k = 0; k < kPerLane; ++k) w4[k] = load_bounds(sb, k * 32 + lane);
                 const GlobalViews GV{ P.views + (size_t)world * F };
                 const ConstViews CV{ VS };
-                if (WORLDS) cull_planes<kPerLane>(GV, v, w4, pass); else cull_planes<kPerLane>(CV, v, w4, pass);
-                const float4 dp = WORLDS ? GV.depth(v) : CV.depth(v);
-                const float ds = WORLDS ? GV.depth_scale(v) : CV.depth_scale(v);
+                const SmemViews SV{ vcache };
+                float4 dp;
+                float ds;
+                if (WORLDS && wcache) { cull_planes<kPerLane>(SV, v, w4, pass); dp = SV.depth(v); ds = SV.depth_scale(v); }
+                else if (WORLDS) { cull_planes<kPerLane>(GV, v, w4, pass); dp = GV.depth(v); ds = GV.depth_scale(v); }
+                else { cull_planes<kPerLane>(CV, v, w4, pass); dp = CV.depth(v); ds = CV.depth_scale(v); }
+                uint32_t view_total = 0;
 #pragma unroll
                 for (int k = 0; k < kPerLane; ++k) {
                     unsigned long long key = 0;
                     if (pass[k]) {
                         key = make_key(P.world_bits, world, v, (meta[k] >> 11) & 255u, meta[k] & 2047u,
                                        depth14(w4[k], dp, ds), local[k]);
-                        if (WORLDS) atomicAdd(&P.counts[(size_t)world * F + v], 1u);
+                        if (WORLDS && !wcache) atomicAdd(&P.counts[(size_t)world * F + v], 1u);
                     }
-                    const uint32_t c = sink.append(pass[k], key);
-                    if (!WORLDS && lane == 0 && c) atomicAdd(&s_counts[v], c);
+                    view_total += sink.append(pass[k], key);
+                }
+                if (lane == 0 && view_total) {
+                    if (!WORLDS) atomicAdd(&s_counts[v], view_total);
+                    else if (wcache) atomicAdd(&P.counts[(size_t)world * F + v], view_total);
                 }
             } else {
                 // sparse: queue (entity, view) tasks; a full round runs as soon as 32 are waiting

@@ -84,6 +84,7 @@ struct FrameParams {
     uint32_t n_worlds;
     uint32_t entities_per_world;
     uint32_t world_bits;
+    uint32_t world_cache;          // batched worlds: 1 = warp tiles never straddle worlds and F fits the per-warp view cache
 };
 
 __device__ __forceinline__ float f4get(const float4 &v, int k)
