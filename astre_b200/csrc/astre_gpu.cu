@@ -103,6 +103,7 @@ struct astre_gpu_ctx {
     uint64_t launches = 0;
     int fused_blocks_per_sm = 2;
     bool coop_launch = false;        // device supports cooperative launches (multi-level hierarchy launches)
+    bool use_pdl = true;             // programmatic dependent launch for the sort chain (ASTRE_NO_PDL disables)
     uint32_t small_level = 32768;    // hierarchy levels below this many entities take the thread-per-entity kernel (measured: config 2, 0.159 -> 0.139 ms)
     ViewSet h_viewset;               // single-world view records, passed as a kernel parameter
     std::string err;
@@ -412,6 +413,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
         CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         ctx->coop_launch = coop != 0 && !std::getenv("ASTRE_NO_COOP");
         if (const char *m = std::getenv("ASTRE_SMALL_LEVEL")) ctx->small_level = (uint32_t)std::atol(m);
+        if (std::getenv("ASTRE_NO_PDL")) ctx->use_pdl = false;
     }
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     CKC(cudaDeviceSynchronize());
@@ -768,19 +770,38 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     if (sort && plan.n_passes) {
         const uint32_t sort_grid = (uint32_t)ctx->sort_grid;   // co-resident CTAs only (static tile striding)
-        k_sort_scan<<<plan.n_passes, 1024, 0, s>>>(ctx->d_sc, ctx->d_block_hist, ctx->hist_regions, ctx->d_ctl, ctx->max_keys);
+        // programmatic dependent launch: each kernel of the chain is made resident while its predecessor drains
+        // and blocks in cudaGridDependencySynchronize() -- hides the launch latency between the short sort kernels
+        cudaLaunchAttribute pdl;
+        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+        cfg.gridDim = dim3(plan.n_passes); cfg.blockDim = dim3(1024);
+        const unsigned long long cap = ctx->max_keys;
+        CK(cudaLaunchKernelEx(&cfg, k_sort_scan, ctx->d_sc, (const uint32_t *)ctx->d_block_hist, ctx->hist_regions,
+                              (const FrameControl *)ctx->d_ctl, cap));
         CK_LAUNCH();
         for (int p = 0; p < (int)plan.n_passes; ++p) {
-            if (ctx->sort_threads == 256)
-                k_sort_pass<256, 8><<<sort_grid, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
-            else
-                k_sort_pass<1024, 8><<<sort_grid, 1024, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p);
+            cfg.gridDim = dim3(sort_grid);
+            if (ctx->sort_threads == 256) {
+                cfg.blockDim = dim3(256);
+                CK(cudaLaunchKernelEx(&cfg, k_sort_pass<256, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
+            } else {
+                cfg.blockDim = dim3(1024);
+                CK(cudaLaunchKernelEx(&cfg, k_sort_pass<1024, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
+            }
             CK_LAUNCH();
         }
     }
     ctx->last_sort_passes = sort ? plan.n_passes : 0u;
     if (n_counts) {
-        k_scan_counts<<<1, 256, 0, s>>>(ctx->d_counts, ctx->d_offsets, n_counts);
+        cudaLaunchAttribute pdl;
+        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.gridDim = dim3(1); cfg.blockDim = dim3(256);
+        CK(cudaLaunchKernelEx(&cfg, k_scan_counts, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts));
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ctx->ev_end, s));

@@ -91,6 +91,7 @@ k_sort_scan(SortControl *sc, const uint32_t *__restrict__ block_hist, const uint
     __shared__ uint32_t s_part[4][256];
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_full;
+    cudaGridDependencySynchronize();
     const uint32_t p = blockIdx.x;
     const uint32_t n = sort_key_count(ctl, cap);
     const int d = threadIdx.x & 255, g = threadIdx.x >> 8;
@@ -190,8 +191,11 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
 {
     constexpr int kTile = THREADS * ITEMS;
     constexpr int kWarps = THREADS / 32;
-    if (sc->skip[pass]) return;
     __shared__ uint32_t s_whist[kWarps][256];
+    // Programmatic dependent launch: this grid may become resident while the previous kernel of the stream is
+    // still draining; nothing it wrote is touched before this point.
+    cudaGridDependencySynchronize();
+    if (sc->skip[pass]) return;
 
     uint32_t executed = 0;                     // passes before this one that moved the keys
     for (int q = 0; q < pass; ++q) executed += sc->skip[q] ? 0u : 1u;
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(256)
 k_scan_counts(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n)
 {
     __shared__ unsigned long long s_warp[8];
+    cudaGridDependencySynchronize();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t per = (n + 255u) / 256u;
     const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
