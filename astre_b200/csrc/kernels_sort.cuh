@@ -39,7 +39,8 @@ struct SortControl {
     uint32_t tile_counter[kSortPasses];  // dynamic tile ids
     uint32_t n_keys;                     // min(key_total, capacity)
     uint32_t epoch;                      // bumped every frame (< 2^27); tags look-back words
-    uint32_t pad[2];
+    uint32_t n_long;                     // tie runs too long for one thread (k_sort_ties_short -> k_sort_ties_long)
+    uint32_t pad;
 };
 
 // Packs the bits of `varying`, LSB first, into digits of up to 8 bits, each made of up to
@@ -121,7 +122,7 @@ k_sort_scan(SortControl *sc, const uint32_t *__restrict__ block_hist, const uint
         if (d == 0) {
             sc->skip[p] = (s_full || n < 2) ? 1u : 0u;
             sc->tile_counter[p] = 0;
-            if (p == 0) sc->n_keys = n;
+            if (p == 0) { sc->n_keys = n; sc->n_long = 0; }
         }
     }
 }
@@ -296,6 +297,147 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
             const uint32_t idx = wbase + i * 32 + lane;
             if (idx < n) out[s_whist[warp][dig_of[i]] + rank[i]] = key[i];
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Ties (optional mode, ASTRE_SORT_TIES=1; off by default -- it wins 2 % on the sparse headline frame and loses
+// 40 % on a dense one).  The radix passes then run over the bits ABOVE the slot field only (depth, mesh, shader,
+// view, world: 22 live bits in a 16M-entity 5-view frame -> 3 passes instead of 6).  They are stable, so keys that
+// agree on all those bits end up adjacent, in emission order; the full key order additionally wants them
+// ascending in slot.  Such runs are short (a run = same view, shader, mesh AND quantised depth):
+//   k_sort_ties_short  one thread per run head: runs of <= 32 keys are insertion-sorted in place, longer
+//                      ones are queued;
+//   k_sort_ties_long   one CTA per queued run: finds its end by binary search and radix-sorts its slot
+//                      field (8 bits per pass) through the spare key buffer.
+// Correct for any run length; a scene that puts millions of entities into one depth bucket of one mesh
+// degrades to a single CTA sorting that run.
+// ---------------------------------------------------------------------------
+constexpr int kShortRun = 32;
+
+__device__ __forceinline__ uint32_t sort_result_buffer(const SortControl *sc, uint32_t n_passes)
+{
+    uint32_t executed = 0;
+    for (uint32_t q = 0; q < n_passes; ++q) executed += sc->skip[q] ? 0u : 1u;
+    return executed & 1u;
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_ties_short(unsigned long long *__restrict__ buf0, unsigned long long *__restrict__ buf1, SortControl *sc,
+                  const uint32_t n_passes, const uint32_t low_bits, uint32_t *__restrict__ long_list, const uint32_t cap_long)
+{
+    cudaGridDependencySynchronize();
+    unsigned long long *keys = sort_result_buffer(sc, n_passes) ? buf1 : buf0;
+    const uint32_t n = sc->n_keys;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k0 = keys[i];
+        const unsigned long long u = k0 >> low_bits;
+        if (i > 0 && (keys[i - 1] >> low_bits) == u) continue;          // not a run head
+        if (i + 1 >= n || (keys[i + 1] >> low_bits) != u) continue;     // run of one
+        unsigned long long a[kShortRun];
+        a[0] = k0;
+        uint32_t len = 1;
+        while (len < (uint32_t)kShortRun && i + len < n) {
+            const unsigned long long k = keys[i + len];
+            if ((k >> low_bits) != u) break;
+            a[len++] = k;
+        }
+        if (len == (uint32_t)kShortRun && i + len < n && (keys[i + len] >> low_bits) == u) {
+            const uint32_t at = atomicAdd(&sc->n_long, 1u);              // longer than one thread should sort
+            if (at < cap_long) long_list[at] = i;
+            continue;
+        }
+        for (uint32_t x = 1; x < len; ++x) {                             // insertion sort, keys are unique
+            const unsigned long long v = a[x];
+            uint32_t y = x;
+            while (y > 0 && a[y - 1] > v) { a[y] = a[y - 1]; --y; }
+            a[y] = v;
+        }
+        for (uint32_t x = 0; x < len; ++x) keys[i + x] = a[x];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_ties_long(unsigned long long *__restrict__ buf0, unsigned long long *__restrict__ buf1, SortControl *sc,
+                 const uint32_t n_passes, const uint32_t low_bits, const uint32_t low_live_bits,
+                 const uint32_t *__restrict__ long_list, const uint32_t cap_long)
+{
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_whist[8][256];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_end;
+    cudaGridDependencySynchronize();
+    const uint32_t n_long = min(sc->n_long, cap_long);
+    if (n_long == 0) return;
+    const uint32_t res = sort_result_buffer(sc, n_passes);
+    unsigned long long *keys = res ? buf1 : buf0, *spare = res ? buf0 : buf1;
+    const uint32_t n = sc->n_keys;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (uint32_t r = blockIdx.x; r < n_long; r += gridDim.x) {
+        const uint32_t start = long_list[r];
+        if (threadIdx.x == 0) {                       // end of the run: first index whose upper bits differ
+            const unsigned long long u = keys[start] >> low_bits;
+            uint32_t lo = start + 1, hi = n;          // keys are sorted by upper bits: binary search
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if ((keys[mid] >> low_bits) == u) lo = mid + 1; else hi = mid;
+            }
+            s_end = lo;
+        }
+        __syncthreads();
+        const uint32_t len = s_end - start;
+        unsigned long long *src = keys + start, *dst = spare + start;
+        uint32_t passes = 0;
+        for (uint32_t shift = 0; shift < low_live_bits; shift += 8, ++passes) {
+            s_hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < len; i += 256) atomicAdd(&s_hist[(uint32_t)(src[i] >> shift) & 255u], 1u);
+            __syncthreads();
+            {   // exclusive scan of the 256 bins -> running output offsets
+                const uint32_t c = s_hist[threadIdx.x];
+                const uint32_t incl = warp_incl_scan(c, lane);
+                if (lane == 31) s_warp[warp] = incl;
+                __syncthreads();
+                uint32_t off = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) if (w < warp) off += s_warp[w];
+                s_hist[threadIdx.x] = off + incl - c;
+            }
+            __syncthreads();
+            // stable scatter, 256 keys at a time: warp ranks (ballot match), warp order, running offsets
+            for (uint32_t base = 0; base < len; base += 256) {
+                for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_whist[0][0])[i] = 0;
+                __syncthreads();
+                const uint32_t i = base + threadIdx.x;
+                const bool valid = i < len;
+                const unsigned long long k = valid ? src[i] : 0ull;
+                const uint32_t dig = (uint32_t)(k >> shift) & 255u;
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                const uint32_t peers = match_digit<true>(dig) & vmask;
+                const uint32_t rank = __popc(peers & lt_mask);
+                if (valid && rank == 0) s_whist[warp][dig] = __popc(peers);
+                __syncthreads();
+                uint32_t before = 0;                  // keys of earlier warps of this chunk with my digit
+                for (int w = 0; w < warp; ++w) before += s_whist[w][dig];
+                if (valid) dst[s_hist[dig] + before + rank] = k;
+                __syncthreads();
+                {   // advance the running offsets by this chunk's counts
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) c += s_whist[w][threadIdx.x];
+                    s_hist[threadIdx.x] += c;
+                }
+                __syncthreads();
+            }
+            unsigned long long *t = src; src = dst; dst = t;
+            __syncthreads();
+        }
+        if (passes & 1u) {                            // the sorted run sits in the spare buffer: copy it home
+            for (uint32_t i = threadIdx.x; i < len; i += 256) keys[start + i] = spare[start + i];
+        }
+        __syncthreads();
     }
 }
 

@@ -299,3 +299,31 @@ def test_stress_moving_camera_and_dirty_sets(oracle):
                 assert np.array_equal(keys, o_keys), it
             else:
                 assert np.all(keys[1:] > keys[:-1]) and counts.sum() == len(keys)
+
+
+@pytest.mark.parametrize("ties", ["0", "1"])
+def test_sort_ties_long_runs(oracle, ties, monkeypatch):
+    """ASTRE_SORT_TIES=1 (optional sort mode) and the default full sort on a scene made of ties.  Keys that agree on everything above the slot field (same view, shader, mesh and depth bucket) are ordered
+    by the tie fix-up: short runs by one thread, runs longer than 32 by one CTA each.  Entities stacked at a few
+    positions make runs of every length, including one of 40k keys."""
+    if ties == "1":
+        monkeypatch.setenv("ASTRE_SORT_TIES", "1")
+    else:
+        monkeypatch.delenv("ASTRE_SORT_TIES", raising=False)
+    n = 100_000
+    s = scenes.config1(n)
+    rng = np.random.default_rng(17)
+    spots = np.array([[0, 5, -20], [3, 5, -40], [-6, 4, -80], [10, 8, -200]], np.float32)
+    group = np.zeros(n, np.int64)
+    group[40_000:70_000] = 1
+    group[70_000:70_040] = 2            # 40 keys per (shader, mesh) class -> short and barely-long runs
+    group[70_040:] = 3
+    s.pos = spots[group].copy()
+    s.pos[90_000:] += rng.normal(scale=30.0, size=(n - 90_000, 3)).astype(np.float32)   # a spread-out tail
+    s.rot[:] = np.array([0, 0, 0, 1], np.float32)
+    s.scale[:] = 1.0
+    s.mesh[:40_000] = 0                 # one class: a single run of ~37k keys (every 16th is invisible)
+    s.shader[:40_000] = 0
+    s.flags = gpu.make_flags(np.arange(n) % 16 != 15, np.full(n, 5, np.uint8))
+    n_keys = check_scene(oracle, s)
+    assert n_keys > 80_000
