@@ -32,6 +32,7 @@
 namespace astre {
 
 constexpr int kSortThreads = 256;
+constexpr uint32_t kReorderMinKeys = 1u << 20;         // from here on a pass is bandwidth-bound: reorder tiles in shared memory
 constexpr int kSortWarps = kSortThreads / 32;
 struct SortControl {
     uint32_t hist[kSortPasses][256];     // exclusive prefixes per digit (k_sort_scan)
@@ -193,6 +194,8 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
     constexpr int kTile = THREADS * ITEMS;
     constexpr int kWarps = THREADS / 32;
     __shared__ uint32_t s_whist[kWarps][256];
+    __shared__ uint32_t s_gbase[256], s_dstart[256], s_wtot[8];
+    __shared__ unsigned long long s_keys[THREADS == 256 ? kTile : 1];
     // Programmatic dependent launch: this grid may become resident while the previous kernel of the stream is
     // still draining; nothing it wrote is touched before this point.
     cudaGridDependencySynchronize();
@@ -246,6 +249,7 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
         __syncthreads();
 
         // thread d < 256: digit d.  Exclusive prefix over the warps, tile total, look-back.
+        uint32_t my_run = 0;
         if (threadIdx.x < 256) {
             const int d = threadIdx.x;
             uint32_t run = 0;
@@ -255,6 +259,7 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
                 s_whist[w][d] = run;
                 run += c;
             }
+            my_run = run;
             unsigned long long *mine = lookback + (size_t)tile * 256 + d;
             uint32_t excl = 0;
             if (tile == 0) {
@@ -286,16 +291,41 @@ k_sort_pass(unsigned long long *__restrict__ buf0, unsigned long long *__restric
                 }
                 st_relaxed(mine, epoch | kFlagPrefix | (unsigned long long)(excl + run));
             }
-            const uint32_t base = sc->hist[pass][d] + excl;
-#pragma unroll 8
-            for (int w = 0; w < kWarps; ++w) s_whist[w][d] += base;
+            s_gbase[d] = sc->hist[pass][d] + excl;
         }
-        __syncthreads();
 
+        if (THREADS == 256 && n >= kReorderMinKeys) {
+            // Bandwidth regime: order the tile by digit in shared memory first, so that consecutive threads
+            // write consecutive keys of a digit (runs of full sectors instead of scattered 8-byte stores).
+            {
+                const uint32_t incl = warp_incl_scan(my_run, lane);       // tile-local start of every digit
+                if (lane == 31) s_wtot[warp] = incl;
+                __syncthreads();
+                uint32_t off = 0;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const uint32_t idx = wbase + i * 32 + lane;
-            if (idx < n) out[s_whist[warp][dig_of[i]] + rank[i]] = key[i];
+                for (int w = 0; w < 8; ++w) if (w < warp) off += s_wtot[w];
+                s_dstart[threadIdx.x] = off + incl - my_run;
+            }
+            __syncthreads();
+            const uint32_t tile_keys = min((uint32_t)kTile, n - tile * kTile);
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t idx = wbase + i * 32 + lane;
+                if (idx < n) s_keys[s_dstart[dig_of[i]] + s_whist[warp][dig_of[i]] + rank[i]] = key[i];
+            }
+            __syncthreads();
+            for (uint32_t j = threadIdx.x; j < tile_keys; j += THREADS) {
+                const unsigned long long k = s_keys[j];
+                const uint32_t dg = digit.of(k);
+                out[s_gbase[dg] + (j - s_dstart[dg])] = k;
+            }
+        } else {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const uint32_t idx = wbase + i * 32 + lane;
+                if (idx < n) out[s_gbase[dig_of[i]] + s_whist[warp][dig_of[i]] + rank[i]] = key[i];
+            }
         }
     }
 }
