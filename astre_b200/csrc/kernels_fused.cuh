@@ -39,6 +39,8 @@ constexpr int kDenseMin = 40;                              // survivors per view
 constexpr int kWorldCacheViews = 1;                        // batched worlds: view records of the warp's world, fetched with the tile
 constexpr int kWarpSmemBytes = kInBytesHier + kStageBytes + kKeyCap * 8 + kQueueCap * 2 + 2 * kWorldCacheViews * 256;   // 12576 (cache is double-buffered)
 constexpr int kFusedSmemBytes = kWarpsPerBlock * kWarpSmemBytes;                           // 100608
+constexpr bool kL2Ahead = false;        // cp.async.bulk.prefetch.L2 of the tile after next: measured r1, no change (0.3376 vs 0.338 ms)
+                                        // -- the 1-deep smem pipeline already hides read latency; the ceiling is resident threads per SM
 constexpr uint32_t kSmemMeshes = 64;    // bounds tables up to this size are served from shared memory
 constexpr uint32_t kSmemViews = 12;     // views up to this index can take the task path
 
@@ -56,6 +58,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// Hint the L2 to fetch a tile record ahead of the bulk copy that will need it (no shared memory involved).
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -305,6 +312,9 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
             mbar_expect_tx(bar, kInBytes);
             bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
         }
+        // the warp's tile after this one: start it towards L2 now (more bytes in flight without more shared memory)
+        if (kL2Ahead && tile + gridDim.x < n_tiles)
+            bulk_prefetch_l2(P.tiles + (size_t)((wb0 + gridDim.x * kBlockTile) >> 7) * kTileFloats, kInBytes);
     };
     if (blockIdx.x < n_tiles && lane == 0) issue(blockIdx.x, parity);
 
