@@ -64,6 +64,18 @@ SIGNATURES = {
     "astre_gpu_device_world": (_P, [_P]),
     "astre_gpu_device_counts": (_P, [_P]),
     "astre_gpu_device_sorted_keys": (_P, [_P]),
+    "astre_gpu_publish_keys": (C.c_int, [_P, C.c_uint32, _P]),
+    "astre_gpu_device_published_keys": (_P, [_P, C.c_uint32]),
+    "astre_gpu_export_handle": (C.c_int, [_P, C.c_uint32, _P]),
+    "astre_gpu_import_handle": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "astre_gpu_release_import": (C.c_int, [_P, _P]),
+    "astre_gpu_merge_lists": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), _U64, C.c_uint64, C.c_uint64, _P]),
+    "astre_gpu_merge_prepare": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P), _U64, _P]),
+    "astre_gpu_merge_published": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), _U64, C.c_uint64, C.c_uint64, _P]),
+    "astre_gpu_device_merged_keys": (_P, [_P]),
+    "astre_gpu_device_merged_sources": (_P, [_P]),
+    "astre_gpu_read_merged": (C.c_int, [_P, C.c_uint64, C.c_uint64, _U64, C.POINTER(C.c_uint8)]),
+    "astre_gpu_last_merge_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "astre_camera_matrices": (None, [_F, _F, _F, C.c_float, C.c_float, C.c_float, C.c_float, _F, _F, _F]),
     "astre_light_space_matrix": (C.c_int, [_F, _F, C.c_int, C.c_float, _F]),
     "astre_ortho_view_matrix": (None, [_F, _F, _F, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F]),

@@ -13,6 +13,7 @@
 
 #include "../../include/astre_gpu.h"
 #include "host_math.hpp"
+#include "kernels_merge.cuh"
 #include "kernels_mirror.cuh"
 #include "kernels_sort.cuh"
 #include "kernels_transform.cuh"
@@ -78,6 +79,20 @@ struct astre_gpu_ctx {
     uint32_t cap_heads = 0;
     uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
     uint32_t epoch = 0;
+
+    // f3: global draw list across GPUs
+    unsigned char *d_publish[2] = {nullptr, nullptr};        // keys | samples | cut table at a fixed address: what peers map
+    uint32_t *d_mcuts = nullptr;                             // scratch of astre_gpu_merge_lists: cut tables
+    uint32_t cap_msamples = 0;
+    unsigned long long *d_merged_keys = nullptr;
+    uint8_t *d_merged_src = nullptr;
+    uint64_t cap_merged = 0, n_merged = 0;
+    uint32_t *d_splits = nullptr, *d_tile_start = nullptr;
+    uint32_t cap_merge_tiles = 0;
+    std::vector<void *> imports;
+    cudaEvent_t ev_merge0 = nullptr, ev_merge1 = nullptr;
+    cudaStream_t merge_stream = nullptr;
+    bool merge_done = false;
 
     // staging for uploads
     unsigned char *d_stage = nullptr;    // two staging halves of stage_entities * 64 bytes
@@ -436,9 +451,12 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads, ctx->d_long_runs };
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads, ctx->d_long_runs,
+                     ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
+                     ctx->d_mcuts };
     for (void *p : ptrs) if (p) cudaFree(p);
-    cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end };
+    for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
+    cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1 };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -1046,6 +1064,277 @@ void *astre_gpu_device_sorted_keys(astre_gpu_ctx *ctx)
 {
     if (!ctx || cache_results(ctx) != ASTRE_OK) return nullptr;
     return ctx->d_keys[ctx->h_result_buf];
+}
+
+// ---- f3: global key-sorted draw list across GPUs ----------------------------
+
+namespace {
+
+// Publish buffer: keys[max_keys] | samples[max_keys/128 + 1] | cuts[kMaxLists * (max_keys/128 + 1)].
+// Every rank of a job uses the same max_keys, so every rank knows every peer's layout.
+struct PublishLayout { size_t samples_off, cuts_off, bytes; uint32_t sample_cap; };
+PublishLayout publish_layout(uint64_t max_keys)
+{
+    PublishLayout P;
+    P.sample_cap = (uint32_t)(max_keys / kSampleStep + 1);
+    P.samples_off = (std::max<uint64_t>(max_keys, 1) * 8 + 255) / 256 * 256;
+    P.cuts_off = P.samples_off + ((size_t)P.sample_cap * 8 + 255) / 256 * 256;
+    P.bytes = P.cuts_off + (size_t)kMaxLists * P.sample_cap * 4;
+    return P;
+}
+
+int ensure_publish(astre_gpu_ctx *ctx, uint32_t parity)
+{
+    if (ctx->d_publish[parity]) return ASTRE_OK;
+    void *p = nullptr;
+    CK(cudaMalloc(&p, publish_layout(ctx->max_keys).bytes));
+    ctx->d_publish[parity] = static_cast<unsigned char *>(p);
+    return ASTRE_OK;
+}
+
+int fill_lists(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_lists, const uint64_t *counts)
+{
+    if (n_lists == 0 || n_lists > (uint32_t)kMaxLists) return fail(ctx, ASTRE_ERR_INVALID, "n_lists must be in 1..%d", kMaxLists);
+    if (ctx->world_bits) return fail(ctx, ASTRE_ERR_STATE, "batched worlds shard by whole worlds: their global list is the rank-major concatenation, no merge");
+    L = MergeLists{};
+    L.n_lists = n_lists;
+    L.slot_bits = ASTRE_KEY_SLOT_BITS;
+    uint64_t total = 0;
+    uint32_t n_samples = 0;
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        if (counts[t] > (1ull << ASTRE_KEY_SLOT_BITS) * ASTRE_MAX_VIEWS) return fail(ctx, ASTRE_ERR_INVALID, "list %u: count out of range", t);
+        L.n[t] = (uint32_t)counts[t];
+        L.sample_base[t] = n_samples;
+        n_samples += (uint32_t)((counts[t] + kSampleStep - 1) >> kSampleShift);
+        total += counts[t];
+    }
+    if (total >= (1ull << 24) * kSampleStep) return fail(ctx, ASTRE_ERR_CAPACITY, "global list of %llu keys exceeds 2^31", (unsigned long long)total);
+    L.sample_base[n_lists] = n_samples;
+    L.total = total;
+    return ASTRE_OK;
+}
+
+// table + tiles, given lists, samples and cut tables
+int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint64_t out_count, cudaStream_t s)
+{
+    const uint32_t n_samples = L.sample_base[L.n_lists];
+    out_first = std::min<uint64_t>(out_first, L.total);
+    out_count = std::min<uint64_t>(out_count, L.total - out_first);
+    if (ctx->cap_merged < out_count || !ctx->d_merged_keys) {
+        if (ctx->d_merged_keys) CK(cudaFree(ctx->d_merged_keys));
+        if (ctx->d_merged_src) CK(cudaFree(ctx->d_merged_src));
+        ctx->d_merged_keys = nullptr; ctx->d_merged_src = nullptr; ctx->cap_merged = 0;
+        const uint64_t cap = std::max<uint64_t>(out_count + out_count / 4, 1024);
+        CK(cudaMalloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_merged_src, cap));
+        ctx->cap_merged = cap;
+    }
+    if (ctx->cap_merge_tiles < n_samples + 1 || !ctx->d_splits) {
+        if (ctx->d_splits) CK(cudaFree(ctx->d_splits));
+        if (ctx->d_tile_start) CK(cudaFree(ctx->d_tile_start));
+        ctx->d_splits = nullptr; ctx->d_tile_start = nullptr; ctx->cap_merge_tiles = 0;
+        const uint32_t cap = n_samples + n_samples / 4 + 64;
+        CK(cudaMalloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
+        ctx->cap_merge_tiles = cap;
+    }
+    if (n_samples && out_count) {
+        k_merge_table<<<ceil_div(((uint64_t)n_samples + 1) * 8, 256), 256, 0, s>>>(L, ctx->d_splits, ctx->d_tile_start);
+        CK_LAUNCH();
+        const uint32_t span = (uint32_t)kMergeBatchKeys - (L.n_lists << kSampleShift);
+        k_merge_tiles<<<ceil_div(L.total, span), kMergeThreads, 0, s>>>(L, ctx->d_splits, ctx->d_tile_start, ctx->d_merged_keys,
+                                                                        ctx->d_merged_src, out_first, out_count);
+        CK_LAUNCH();
+    }
+    CK(cudaEventRecord(ctx->ev_merge1, s));
+    ctx->n_merged = out_count;
+    ctx->merge_stream = s;
+    ctx->merge_done = true;
+    return ASTRE_OK;
+}
+
+int merge_begin(astre_gpu_ctx *ctx, cudaStream_t s)
+{
+    if (!ctx->ev_merge0) {
+        CK(cudaEventCreate(&ctx->ev_merge0));
+        CK(cudaEventCreate(&ctx->ev_merge1));
+    }
+    CK(cudaEventRecord(ctx->ev_merge0, s));
+    return ASTRE_OK;
+}
+
+}  // namespace
+
+int astre_gpu_publish_keys(astre_gpu_ctx *ctx, uint32_t parity, void *stream)
+{
+    if (!ctx || parity > 1) return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_publish(ctx, parity)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    unsigned char *base = ctx->d_publish[parity];
+    k_publish_keys<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc->skip, ctx->last_sort_passes,
+                                                     &ctx->d_ctl->key_total, ctx->max_keys,
+                                                     reinterpret_cast<unsigned long long *>(base),
+                                                     reinterpret_cast<unsigned long long *>(base + publish_layout(ctx->max_keys).samples_off));
+    CK_LAUNCH();
+    return ASTRE_OK;
+}
+
+void *astre_gpu_device_published_keys(astre_gpu_ctx *ctx, uint32_t parity)
+{
+    if (!ctx || parity > 1) return nullptr;
+    cudaSetDevice(ctx->device);
+    return ensure_publish(ctx, parity) == ASTRE_OK ? ctx->d_publish[parity] : nullptr;
+}
+
+int astre_gpu_export_handle(astre_gpu_ctx *ctx, uint32_t parity, void *handle_out)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == ASTRE_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ctx || parity > 1 || !handle_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = ensure_publish(ctx, parity)) return rc;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->d_publish[parity]));
+    std::memcpy(handle_out, &h, sizeof h);
+    return ASTRE_OK;
+}
+
+int astre_gpu_import_handle(astre_gpu_ctx *ctx, const void *handle, void **dev_ptr)
+{
+    if (!ctx || !handle || !dev_ptr) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->imports.push_back(p);
+    *dev_ptr = p;
+    return ASTRE_OK;
+}
+
+int astre_gpu_release_import(astre_gpu_ctx *ctx, void *dev_ptr)
+{
+    if (!ctx || !dev_ptr) return ASTRE_ERR_INVALID;
+    auto it = std::find(ctx->imports.begin(), ctx->imports.end(), dev_ptr);
+    if (it == ctx->imports.end()) return fail(ctx, ASTRE_ERR_INVALID, "pointer was not returned by astre_gpu_import_handle");
+    CK(cudaSetDevice(ctx->device));
+    ctx->imports.erase(it);
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return ASTRE_OK;
+}
+
+int astre_gpu_merge_lists(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *lists, const uint64_t *counts,
+                          uint64_t out_first, uint64_t out_count, void *stream)
+{
+    if (!ctx || !lists || !counts) return ASTRE_ERR_INVALID;
+    MergeLists L;
+    if (int rc = fill_lists(ctx, L, n_lists, counts)) return rc;
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        if (counts[t] && !lists[t]) return fail(ctx, ASTRE_ERR_INVALID, "list %u is null", t);
+        L.keys[t] = static_cast<const unsigned long long *>(lists[t]);
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n_samples = L.sample_base[n_lists];
+    if (ctx->cap_msamples < n_samples || !ctx->d_mcuts) {
+        if (ctx->d_mcuts) CK(cudaFree(ctx->d_mcuts));
+        ctx->d_mcuts = nullptr; ctx->cap_msamples = 0;
+        const uint32_t cap = n_samples + n_samples / 4 + 64;
+        CK(cudaMalloc(&ctx->d_mcuts, (size_t)cap * kMaxLists * 4));
+        ctx->cap_msamples = cap;
+    }
+    if (int rc = merge_begin(ctx, s)) return rc;
+    L.sample_stride_shift = kSampleShift;                  // samples are read straight out of the lists
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        L.samples[t] = L.keys[t];
+        L.cuts[t] = ctx->d_mcuts + (size_t)t * ctx->cap_msamples;
+    }
+    if (n_samples) {
+        dim3 grid(std::min<uint32_t>(ceil_div(n_samples, 256), (uint32_t)ctx->sm_count * 8), n_lists);
+        k_merge_cuts<<<grid, 256, 0, s>>>(L, 0u, ctx->d_mcuts, (size_t)ctx->cap_msamples);
+        CK_LAUNCH();
+    }
+    return merge_tail(ctx, L, out_first, out_count, s);
+}
+
+// Peer-to-peer flow, step 1 (after the counts exchange): rank `rank` ranks every sample of every
+// published list inside its own list and leaves the cut table in its publish buffer.
+int astre_gpu_merge_prepare(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish, const uint64_t *counts,
+                            void *stream)
+{
+    if (!ctx || !publish || !counts || rank >= n_lists) return ASTRE_ERR_INVALID;
+    MergeLists L;
+    if (int rc = fill_lists(ctx, L, n_lists, counts)) return rc;
+    const PublishLayout P = publish_layout(ctx->max_keys);
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        if (!publish[t]) return fail(ctx, ASTRE_ERR_INVALID, "publish buffer %u is null", t);
+        if (counts[t] > ctx->max_keys) return fail(ctx, ASTRE_ERR_CAPACITY, "list %u has %llu keys; publish buffers hold %llu (every rank must use the same max_keys)",
+                                                    t, (unsigned long long)counts[t], (unsigned long long)ctx->max_keys);
+        const unsigned char *base = static_cast<const unsigned char *>(publish[t]);
+        L.keys[t] = reinterpret_cast<const unsigned long long *>(base);
+        L.samples[t] = reinterpret_cast<const unsigned long long *>(base + P.samples_off);
+        L.cuts[t] = reinterpret_cast<const uint32_t *>(base + P.cuts_off);
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (int rc = merge_begin(ctx, s)) return rc;
+    const uint32_t n_samples = L.sample_base[n_lists];
+    if (n_samples) {
+        uint32_t *own_cuts = const_cast<uint32_t *>(L.cuts[rank]);
+        k_merge_cuts<<<std::min<uint32_t>(ceil_div(n_samples, 256), (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(L, rank, own_cuts, 0);
+        CK_LAUNCH();
+    }
+    return ASTRE_OK;
+}
+
+// Step 2 (after a barrier that orders every rank's astre_gpu_merge_prepare before it): tile table
+// from all cut tables, then the merge itself, reading keys straight from the peers' buffers.
+int astre_gpu_merge_published(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish, const uint64_t *counts,
+                              uint64_t out_first, uint64_t out_count, void *stream)
+{
+    if (!ctx || !publish || !counts) return ASTRE_ERR_INVALID;
+    MergeLists L;
+    if (int rc = fill_lists(ctx, L, n_lists, counts)) return rc;
+    const PublishLayout P = publish_layout(ctx->max_keys);
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        if (!publish[t]) return fail(ctx, ASTRE_ERR_INVALID, "publish buffer %u is null", t);
+        if (counts[t] > ctx->max_keys) return fail(ctx, ASTRE_ERR_CAPACITY, "list %u has %llu keys; publish buffers hold %llu", t,
+                                                    (unsigned long long)counts[t], (unsigned long long)ctx->max_keys);
+        const unsigned char *base = static_cast<const unsigned char *>(publish[t]);
+        L.keys[t] = reinterpret_cast<const unsigned long long *>(base);
+        L.samples[t] = reinterpret_cast<const unsigned long long *>(base + P.samples_off);
+        L.cuts[t] = reinterpret_cast<const uint32_t *>(base + P.cuts_off);
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (!ctx->ev_merge0) { if (int rc = merge_begin(ctx, s)) return rc; }
+    return merge_tail(ctx, L, out_first, out_count, s);
+}
+
+void *astre_gpu_device_merged_keys(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_keys : nullptr; }
+void *astre_gpu_device_merged_sources(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_src : nullptr; }
+
+int astre_gpu_read_merged(astre_gpu_ctx *ctx, uint64_t first, uint64_t n, uint64_t *keys, uint8_t *sources)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (!ctx->merge_done) return fail(ctx, ASTRE_ERR_STATE, "no merge has been run");
+    if (first + n > ctx->n_merged) return fail(ctx, ASTRE_ERR_INVALID, "range [%llu, %llu) exceeds the %llu merged keys",
+                                              (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)ctx->n_merged);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->merge_stream));
+    if (n && keys) CK(cudaMemcpy(keys, ctx->d_merged_keys + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n && sources) CK(cudaMemcpy(sources, ctx->d_merged_src + first, n, cudaMemcpyDeviceToHost));
+    return ASTRE_OK;
+}
+
+int astre_gpu_last_merge_ms(astre_gpu_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return ASTRE_ERR_INVALID;
+    if (!ctx->merge_done) return fail(ctx, ASTRE_ERR_STATE, "no merge has been run");
+    CK(cudaEventSynchronize(ctx->ev_merge1));
+    CK(cudaEventElapsedTime(ms, ctx->ev_merge0, ctx->ev_merge1));
+    return ASTRE_OK;
 }
 
 // ---- host-side helpers -------------------------------------------------------

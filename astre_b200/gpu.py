@@ -208,6 +208,71 @@ class GpuContext:
         self._check(self._lib.astre_gpu_slot_entity(self._h, int(slot), C.byref(e)))
         return e.value
 
+    # ---- f3: global key-sorted draw list across GPUs ----
+    def publish_keys(self, parity, stream=None):
+        """Copy the frame's sorted list into publish buffer `parity` (fixed address, what peers map)."""
+        self._check(self._lib.astre_gpu_publish_keys(self._h, int(parity), stream))
+
+    def device_published_keys_ptr(self, parity):
+        return self._lib.astre_gpu_device_published_keys(self._h, int(parity))
+
+    def device_sorted_keys_ptr(self):
+        return self._lib.astre_gpu_device_sorted_keys(self._h)
+
+    def export_handle(self, parity):
+        """CUDA IPC handle (bytes) of publish buffer `parity`."""
+        buf = (C.c_ubyte * 64)()
+        self._check(self._lib.astre_gpu_export_handle(self._h, int(parity), buf))
+        return bytes(buf)
+
+    def import_handle(self, handle):
+        """Map a peer's publish buffer; returns the device pointer (int)."""
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self._check(self._lib.astre_gpu_import_handle(self._h, buf, C.byref(out)))
+        return out.value
+
+    def release_import(self, ptr):
+        self._check(self._lib.astre_gpu_release_import(self._h, C.c_void_p(ptr)))
+
+    def merge_lists(self, list_ptrs, counts, out_first=0, out_count=None, stream=None):
+        """Merge the ranks' sorted lists (device pointers, list r = rank r) into the global draw list,
+        keeping positions [out_first, out_first + out_count)."""
+        g = len(list_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in list_ptrs])
+        cnt = np.ascontiguousarray(counts, np.uint64)
+        oc = 0xFFFFFFFFFFFFFFFF if out_count is None else int(out_count)
+        self._check(self._lib.astre_gpu_merge_lists(self._h, g, ptrs, _ptr(cnt, C.c_uint64), int(out_first), oc, stream))
+
+    def merge_prepare(self, rank, publish_ptrs, counts, stream=None):
+        """Peer-to-peer flow, step 1: rank every sample of every published list inside this rank's own list."""
+        g = len(publish_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in publish_ptrs])
+        cnt = np.ascontiguousarray(counts, np.uint64)
+        self._check(self._lib.astre_gpu_merge_prepare(self._h, g, int(rank), ptrs, _ptr(cnt, C.c_uint64), stream))
+
+    def merge_published(self, publish_ptrs, counts, out_first=0, out_count=None, stream=None):
+        """Peer-to-peer flow, step 2 (after a barrier): tile table from all cut tables + the merge."""
+        g = len(publish_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in publish_ptrs])
+        cnt = np.ascontiguousarray(counts, np.uint64)
+        oc = 0xFFFFFFFFFFFFFFFF if out_count is None else int(out_count)
+        self._check(self._lib.astre_gpu_merge_published(self._h, g, ptrs, _ptr(cnt, C.c_uint64), int(out_first), oc, stream))
+
+    def read_merged(self, first, n):
+        keys = np.empty(int(n), np.uint64)
+        src = np.empty(int(n), np.uint8)
+        self._check(self._lib.astre_gpu_read_merged(self._h, int(first), int(n), _ptr(keys, C.c_uint64), _ptr(src, C.c_uint8)))
+        return keys, src
+
+    def device_merged_ptrs(self):
+        return self._lib.astre_gpu_device_merged_keys(self._h), self._lib.astre_gpu_device_merged_sources(self._h)
+
+    def last_merge_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.astre_gpu_last_merge_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def device_counts_ptr(self):
         return self._lib.astre_gpu_device_counts(self._h)
 

@@ -38,3 +38,79 @@ def segment_offsets(all_counts, rank):
     (view, rank, key), and the per-view totals."""
     a = all_counts.detach().cpu().numpy().astype(np.uint32)
     return _gpu.global_offsets(a, rank)
+
+
+def device_view(ptr, n, typestr, device):
+    """Zero-copy torch view of `n` elements of library-owned device memory."""
+    class _View:
+        __cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_View(), device=device)
+
+
+class GlobalDrawList:
+    """f3: one globally key-sorted draw list out of the ranks' sorted lists, ordered
+    (key >> 26, rank, local slot) = class, depth, global entity order (flat scenes sharded by range).
+
+    mode "p2p":  every rank publishes its list at a fixed device address, the addresses are exchanged
+                 once as CUDA IPC handles, and the merge kernel reads the peers' lists over NVLink
+                 itself -- the exchange is fused into the merge, no gather buffer, and with
+                 `sliced=True` a rank pulls only the keys of its own slice of the global list.
+    mode "nccl": all-gather of the (padded) lists, then the same merge kernel on the gathered rows
+                 (the library-collective baseline the p2p mode is measured against).
+    Per frame the only host round trip is reading the all-gathered per-view counts."""
+
+    def __init__(self, ctx, n_views, max_keys, mode="p2p", group=None, device=None):
+        assert mode in ("p2p", "nccl")
+        self.ctx, self.mode, self.group, self.n_views, self.max_keys = ctx, mode, group, n_views, int(max_keys)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.counts_dev = device_view(ctx.device_counts_ptr(), n_views, "<i4", self.device)
+        self.local = [ctx.device_published_keys_ptr(p) for p in (0, 1)]
+        self.local_view = [device_view(self.local[p], self.max_keys, "<i8", self.device) for p in (0, 1)]
+        self.peer = [[None, None] for _ in range(self.world)]
+        self.peer[self.rank] = list(self.local)
+        self._gathered = None
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if mode == "p2p" and self.world > 1:
+            mine = [ctx.export_handle(0), ctx.export_handle(1)]
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.peer[r] = [ctx.import_handle(handles[r][0]), ctx.import_handle(handles[r][1])]
+
+    def build(self, frame_index, sliced=False, stream=None):
+        """Call after ctx.frame().  Returns (all_counts [G, F] on the host, out_first, out_count): the
+        merged keys / sources of positions [out_first, out_first + out_count) are in the library's
+        merge buffers (ctx.read_merged / ctx.device_merged_ptrs)."""
+        parity = frame_index & 1
+        self.ctx.publish_keys(parity, stream)
+        # the counts all-gather is stream-ordered after the publish copy on every rank: once it has
+        # completed here, every peer's published list is complete
+        all_counts = exchange_counts(self.counts_dev, self.group).cpu().numpy().astype(np.uint64)
+        totals = all_counts.sum(axis=1)
+        total = int(totals.sum())
+        if sliced:
+            per = -(-total // self.world)
+            first = min(self.rank * per, total)
+            count = min(per, total - first)
+        else:
+            first, count = 0, total
+        if self.mode == "p2p" or self.world == 1:
+            ptrs = [self.peer[r][parity] for r in range(self.world)]
+            # each rank searches its own list only; the cut tables are read by the peers afterwards
+            self.ctx.merge_prepare(self.rank, ptrs, totals, stream)
+            if self.world > 1:
+                dist.all_reduce(self._token, group=self.group)      # device-side barrier, no host sync
+            self.ctx.merge_published(ptrs, totals, first, count, stream)
+            return all_counts, first, count
+        else:
+            cap = max(int(totals.max()), 1)
+            if self._gathered is None or self._gathered.numel() < self.world * cap:
+                self._gathered = torch.empty(self.world * (cap + cap // 4), dtype=torch.int64, device=self.device)
+            rows = self._gathered[: self.world * cap]
+            dist.all_gather_into_tensor(rows, self.local_view[parity][:cap], group=self.group)
+            ptrs = [rows.data_ptr() + 8 * cap * r for r in range(self.world)]
+        self.ctx.merge_lists(ptrs, totals, first, count, stream)
+        return all_counts, first, count

@@ -225,6 +225,68 @@ ASTRE_API void *astre_gpu_device_world(astre_gpu_ctx *ctx);        /* float[max_
 ASTRE_API void *astre_gpu_device_counts(astre_gpu_ctx *ctx);       /* uint32[n_worlds*views]   */
 ASTRE_API void *astre_gpu_device_sorted_keys(astre_gpu_ctx *ctx);  /* uint64[]; synchronises  */
 
+/* ---- f3: one globally key-sorted draw list across GPUs --
+ *
+ * Spec-defined; the reference has no multi-GPU path.  Rank r owns a contiguous
+ * range of the scene's entities, so the global list is the ranks' sorted lists
+ * merged under the order (key >> slot_bits, rank, key & slot_mask): class and
+ * depth first, then global entity order.  Batched worlds shard by whole worlds;
+ * their global list is the rank-major concatenation already described by
+ * astre_global_offsets and needs no merge.
+ *
+ * Two ways to feed the merge:
+ *  (a) astre_gpu_merge_lists on device pointers this GPU can read at full speed
+ *      (its own list, rows of an all-gathered buffer).
+ *  (b) peer to peer, nothing gathered: every rank publishes its list at a fixed
+ *      device address (astre_gpu_publish_keys: keys, then every 128th key as a
+ *      sample), the addresses are exchanged once as CUDA IPC handles, and per
+ *      frame
+ *        frame(ALL) -> publish_keys -> all-gather of counts (8e; also the barrier
+ *        that completes the peers' publish) -> astre_gpu_merge_prepare (each
+ *        rank ranks all samples inside ITS OWN list: no search crosses NVLink)
+ *        -> any collective as a barrier -> astre_gpu_merge_published (tile table
+ *        from the peers' cut tables, then the merge kernel pulls the peers' keys
+ *        over NVLink itself; with out_first/out_count only this rank's slice).
+ *      Every rank must have been created with the same max_keys. */
+#define ASTRE_MAX_LISTS 8
+#define ASTRE_IPC_HANDLE_BYTES 64
+
+/* Copies the last frame's sorted list (and its samples) into publish buffer
+ * `parity` (0/1, fixed device addresses, capacity max_keys); asynchronous, no
+ * host round trip.
+ * Alternate the parity from frame to frame: a peer may still be reading the
+ * previous frame's buffer. */
+ASTRE_API int astre_gpu_publish_keys(astre_gpu_ctx *ctx, uint32_t parity, void *stream);
+ASTRE_API void *astre_gpu_device_published_keys(astre_gpu_ctx *ctx, uint32_t parity);
+/* CUDA IPC handle (ASTRE_IPC_HANDLE_BYTES bytes) of publish buffer `parity`,
+ * for another process on the same node. */
+ASTRE_API int astre_gpu_export_handle(astre_gpu_ctx *ctx, uint32_t parity, void *handle_out);
+/* Maps a peer's publish buffer into this process; *dev_ptr stays valid until
+ * astre_gpu_release_import or astre_gpu_destroy. */
+ASTRE_API int astre_gpu_import_handle(astre_gpu_ctx *ctx, const void *handle, void **dev_ptr);
+ASTRE_API int astre_gpu_release_import(astre_gpu_ctx *ctx, void *dev_ptr);
+
+/* Merges n_lists (<= ASTRE_MAX_LISTS) sorted key lists, list r being rank r's
+ * (device pointers: local, peer-mapped, or rows of a gathered buffer; counts on
+ * the host), and keeps positions [out_first, out_first+out_count) of the
+ * global list (out_count = UINT64_MAX: everything from out_first on).
+ * Asynchronous on `stream`. */
+ASTRE_API int astre_gpu_merge_lists(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *lists,
+                                    const uint64_t *counts, uint64_t out_first, uint64_t out_count, void *stream);
+/* Peer-to-peer flow, see (b) above.  publish[r] = base of rank r's publish
+ * buffer of this frame's parity (own: astre_gpu_device_published_keys, peers:
+ * astre_gpu_import_handle); counts[r] = rank r's key total. */
+ASTRE_API int astre_gpu_merge_prepare(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish,
+                                      const uint64_t *counts, void *stream);
+ASTRE_API int astre_gpu_merge_published(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish,
+                                        const uint64_t *counts, uint64_t out_first, uint64_t out_count, void *stream);
+/* Result of the last merge: keys[i], sources[i] (= rank) for global position
+ * out_first + i.  read_merged synchronises; `first` is relative to out_first. */
+ASTRE_API void *astre_gpu_device_merged_keys(astre_gpu_ctx *ctx);     /* uint64[] */
+ASTRE_API void *astre_gpu_device_merged_sources(astre_gpu_ctx *ctx);  /* uint8[]  */
+ASTRE_API int astre_gpu_read_merged(astre_gpu_ctx *ctx, uint64_t first, uint64_t n, uint64_t *keys, uint8_t *sources);
+ASTRE_API int astre_gpu_last_merge_ms(astre_gpu_ctx *ctx, float *ms);
+
 /* ---- host-side helpers (no device work) ------------------------------------ */
 
 /* CameraSystem::run's matrices (camera_system.cpp:24-37): view = lookAt(pos, pos+forward, up),

@@ -35,7 +35,7 @@
  *   participation predicate engine/modules/Pipeline/src/deferred_shading.cpp:115-121,151-156
  * Spec-defined parts (the reference has no hierarchy, bounds, frustum test,
  * sort key or sort -- SURVEY.md section 0, Appendix B): orc_transform_hierarchy,
- * orc_extract_view, orc_cull_keys, orc_sort_keys.  Their arithmetic is fixed
+ * orc_extract_view, orc_cull_keys, orc_sort_keys, orc_merge_lists.  Their arithmetic is fixed
  * here and the CUDA path must reproduce it bit for bit.
  */
 #include <math.h>
@@ -662,6 +662,33 @@ ORC_API uint64_t orc_frame(uint32_t n, const float *pos3, const float *rot4, con
                         views_per_world, views, keys, cap, counts);
     orc_sort_keys(keys, total < cap ? total : cap);
     return total;
+}
+
+/* ---- f3: global key-sorted draw list across shards (spec-defined) --
+ *
+ * Shard r holds a contiguous range of the scene's entities and a list sorted by
+ * its own keys.  The global list orders all keys by
+ *     (key >> slot_bits, shard, key & slot_mask)
+ * i.e. class and depth first, then global entity order.  Plain G-way merge by
+ * repeatedly taking the smallest head; out_src[i] = shard of out_keys[i]. */
+ORC_API void orc_merge_lists(uint32_t n_lists, const uint64_t *const *lists, const uint64_t *counts,
+                             uint32_t slot_bits, uint64_t *out_keys, uint8_t *out_src)
+{
+    uint64_t head[64] = {0};
+    uint64_t at = 0;
+    if (n_lists > 64) return;
+    for (;;) {
+        int best = -1;
+        uint64_t best_cls = 0;
+        for (uint32_t t = 0; t < n_lists; ++t) {
+            if (head[t] >= counts[t]) continue;
+            const uint64_t cls = lists[t][head[t]] >> slot_bits;
+            if (best < 0 || cls < best_cls) { best = (int)t; best_cls = cls; }   /* ties: lower shard first */
+        }
+        if (best < 0) break;
+        out_keys[at] = lists[best][head[best]++];
+        out_src[at++] = (uint8_t)best;
+    }
 }
 
 /* ---- f1: interpolateFrame per-proxy step (render.cpp:26-39) ---------------- */

@@ -181,6 +181,19 @@ class Oracle:
                                      _p(pb, C.c_float), _p(rb, C.c_float), _p(sb, C.c_float), _p(world, C.c_float))
         return world
 
+    def merge_lists(self, lists, slot_bits=26):
+        """f3: G sorted lists (list r = shard r) -> global list ordered (key >> slot_bits, shard, slot)."""
+        lists = [np.ascontiguousarray(a, np.uint64) for a in lists]
+        g = len(lists)
+        ptrs = (C.POINTER(C.c_uint64) * g)(*[_p(a, C.c_uint64) for a in lists])
+        counts = np.array([len(a) for a in lists], np.uint64)
+        total = int(counts.sum())
+        keys = np.empty(total, np.uint64)
+        src = np.empty(total, np.uint8)
+        self.lib.orc_merge_lists(C.c_uint32(g), ptrs, _p(counts, C.c_uint64), C.c_uint32(slot_bits),
+                                 _p(keys, C.c_uint64), _p(src, C.c_uint8))
+        return keys, src
+
     def sort_keys(self, keys):
         k = np.ascontiguousarray(keys, np.uint64).copy()
         self.lib.orc_sort_keys(_p(k, C.c_uint64), C.c_uint64(len(k)))

@@ -1,0 +1,175 @@
+"""f3: the globally key-sorted draw list across shards.
+
+CPU part: the oracle's merge against an independent numpy statement of the order
+(key >> slot_bits, shard, key & slot_mask).  GPU part (one GPU holds every shard, in separate
+contexts): astre_gpu_merge_lists against the oracle, and against the property that the merged list
+of G range shards, with (shard, local slot) mapped back to global slots, IS the sorted list of the
+unsharded scene."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from astre_b200 import scenes
+
+SLOT_BITS = 26
+
+
+def np_merge(lists):
+    keys = np.concatenate(lists) if lists else np.empty(0, np.uint64)
+    src = np.concatenate([np.full(len(a), r, np.uint8) for r, a in enumerate(lists)])
+    cls = keys >> np.uint64(SLOT_BITS)
+    local = keys & np.uint64((1 << SLOT_BITS) - 1)
+    order = np.lexsort((local, src, cls))
+    return keys[order], src[order]
+
+
+def random_lists(rng, g, n_max, n_classes):
+    """Sorted lists of unique keys with many class collisions across (and inside) lists."""
+    out = []
+    for _ in range(g):
+        n = int(rng.integers(0, n_max + 1))
+        cls = rng.integers(0, n_classes, n).astype(np.uint64) * np.uint64(977)
+        slot = rng.choice(1 << 20, n, replace=False).astype(np.uint64)
+        out.append(np.sort((cls << np.uint64(SLOT_BITS)) | slot))
+    return out
+
+
+@pytest.mark.parametrize("g,n_max,n_classes", [(1, 100, 5), (2, 1000, 7), (3, 5000, 1), (8, 3000, 50), (8, 20, 3), (4, 0, 1)])
+def test_oracle_merge_matches_numpy(oracle, g, n_max, n_classes):
+    rng = np.random.default_rng(g * 1000 + n_max)
+    lists = random_lists(rng, g, n_max, n_classes)
+    keys, src = oracle.merge_lists(lists, SLOT_BITS)
+    k2, s2 = np_merge(lists)
+    assert np.array_equal(keys, k2) and np.array_equal(src, s2)
+
+
+def test_oracle_merge_of_range_shards_is_the_unsharded_list(oracle):
+    scene = scenes.config3(60_000)
+    _, full_keys, _ = oracle.frame(scene)
+    g = 4
+    lists, bases = [], []
+    per = (-(-scene.n // g) + 3) & ~3
+    for r in range(g):
+        _, k, _ = oracle.frame(scene.shard(r, g))
+        lists.append(k)
+        bases.append(min(r * per, scene.n))
+    keys, src = oracle.merge_lists(lists, SLOT_BITS)
+    glob = keys + np.array(bases, np.uint64)[src]
+    assert np.array_equal(glob, full_keys)
+
+
+# ---- GPU ---------------------------------------------------------------------
+
+def _gpu_shard_lists(scene, g):
+    from astre_b200 import GpuContext
+    ctxs, ptrs, counts, host = [], [], [], []
+    per = max(scene.shard(0, g).n, 1)
+    for r in range(g):
+        sh = scene.shard(r, g)
+        ctx = GpuContext(per, max_views=scene.views_per_world, max_keys=per * scene.views_per_world)   # same max_keys on every "rank"
+        scenes.load_into(ctx, sh)
+        ctx.frame()
+        ctx.publish_keys(r & 1)
+        host.append(ctx.read_all_keys())
+        counts.append(len(host[-1]))
+        ptrs.append(ctx.device_published_keys_ptr(r & 1))
+        ctxs.append(ctx)
+    return ctxs, ptrs, counts, host
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,g", [(200_000, 2), (1_000_000, 8), (50_000, 3), (4_000, 8), (300, 5)])
+def test_gpu_merge_of_range_shards(oracle, n, g):
+    scene = scenes.config3(n)
+    ctxs, ptrs, counts, host = _gpu_shard_lists(scene, g)
+    try:
+        o_keys, o_src = oracle.merge_lists(host, SLOT_BITS)
+        ctxs[0].merge_lists(ptrs, counts)
+        keys, src = ctxs[0].read_merged(0, len(o_keys))
+        assert np.array_equal(keys, o_keys) and np.array_equal(src, o_src)
+        # property: with (shard, local slot) -> global slot this is the unsharded frame's sorted list
+        per = (-(-scene.n // g) + 3) & ~3
+        bases = np.array([min(r * per, scene.n) for r in range(g)], np.uint64)
+        _, full_keys, _ = oracle.frame(scene)
+        assert np.array_equal(keys + bases[src], full_keys)
+        # a rank's slice only
+        total = len(o_keys)
+        lo, hi = total // 3, total // 3 + total // 2
+        ctxs[0].merge_lists(ptrs, counts, out_first=lo, out_count=hi - lo)
+        k2, s2 = ctxs[0].read_merged(0, hi - lo)
+        assert np.array_equal(k2, o_keys[lo:hi]) and np.array_equal(s2, o_src[lo:hi])
+        # the peer-to-peer flow (here every "peer" buffer is on the same GPU): each rank ranks the
+        # samples in its own list, then any rank builds the list from the published cut tables
+        for r in range(g):
+            ctxs[r].merge_prepare(r, ptrs, counts)
+            ctxs[r].sync()
+        last = ctxs[g - 1]
+        last.merge_published(ptrs, counts)
+        k3, s3 = last.read_merged(0, total)
+        assert np.array_equal(k3, o_keys) and np.array_equal(s3, o_src)
+        last.merge_published(ptrs, counts, out_first=lo, out_count=hi - lo)
+        k4, s4 = last.read_merged(0, hi - lo)
+        assert np.array_equal(k4, o_keys[lo:hi]) and np.array_equal(s4, o_src[lo:hi])
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_merge_dense_ties_and_empty_lists(oracle):
+    """All entities visible in every view (long equal-class runs across shards) and shards with no keys."""
+    from astre_b200 import GpuContext, gpu
+    s = scenes.config1(120_000)
+    s.pos = (s.pos * np.float32(0.02)).astype(np.float32)
+    s.pos[:, 2] -= np.float32(40.0)
+    s.mesh[:] = 1
+    s.shader[:] = 1
+    s.flags[:] = gpu.make_flags(np.ones(s.n, bool), np.full(s.n, 5, np.uint8))
+    s.flags[: s.n // 4] = 0            # shard 0 of 4 emits nothing
+    ctxs, ptrs, counts, host = _gpu_shard_lists(s, 4)
+    try:
+        assert counts[0] == 0 and min(counts[1:]) > 0
+        o_keys, o_src = oracle.merge_lists(host, SLOT_BITS)
+        ctxs[1].merge_lists(ptrs, counts)
+        keys, src = ctxs[1].read_merged(0, len(o_keys))
+        assert np.array_equal(keys, o_keys) and np.array_equal(src, o_src)
+        # all lists empty
+        ctxs[1].merge_lists(ptrs, [0, 0, 0, 0])
+        k0, _ = ctxs[1].read_merged(0, 0)
+        assert len(k0) == 0
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_merge_rejects_worlds_and_bad_arguments():
+    from astre_b200 import AstreError, GpuContext
+    s = scenes.config5(8, 256)
+    with GpuContext(s.n, max_views=1) as ctx:
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        ctx.publish_keys(0)
+        with pytest.raises(AstreError):
+            ctx.merge_lists([ctx.device_published_keys_ptr(0)], [1])
+    with GpuContext(1024, max_views=1) as ctx:
+        with pytest.raises(AstreError):
+            ctx.merge_lists([None] * 9, [0] * 9)
+        with pytest.raises(AstreError):
+            ctx.merge_lists([None], [5])
+
+
+@pytest.mark.gpu
+def test_multi_gpu_merge():
+    """Two processes, two GPUs: peers' lists read over NVLink (CUDA IPC) and the NCCL all-gather mode."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(here, "merge_worker.py"), "400000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "MERGE_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
