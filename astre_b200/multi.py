@@ -22,6 +22,41 @@ def shard_worlds(n_worlds, rank, world_size):
     return min(rank * per, n_worlds), min((rank + 1) * per, n_worlds)
 
 
+def shard_subtrees(parent, world_size):
+    """Hierarchies shard by ROOT SUBTREE, so parent-before-child never crosses a GPU.
+    Subtrees, in root order, are dealt to ranks in contiguous groups balanced by node count (to within
+    one subtree).  Returns, per rank, (global entity indices ascending, parent as local slot)."""
+    parent = np.asarray(parent, np.uint32)
+    n = len(parent)
+    idx = np.arange(n, dtype=np.int64)
+    is_root = parent == _gpu.NO_PARENT
+    anc = np.where(is_root, idx, parent.astype(np.int64))
+    if n and (anc.min() < 0 or anc.max() >= n):
+        raise ValueError("parent index out of range")
+    for _ in range(64):                                   # pointer jumping: anc -> root in log2(depth) rounds
+        nxt = anc[anc]
+        if np.array_equal(nxt, anc):
+            break
+        anc = nxt
+    else:
+        raise ValueError("cyclic parent links")
+    if n and not is_root[anc].all():
+        raise ValueError("cyclic parent links")
+    size = np.bincount(anc, minlength=n)                  # nodes per root (0 for non-roots)
+    before = np.cumsum(size) - size                       # nodes of the subtrees that come earlier
+    rank_of_root = np.minimum(before * world_size // max(n, 1), world_size - 1)
+    rank_of = rank_of_root[anc]
+    out = []
+    for r in range(world_size):
+        mine = np.flatnonzero(rank_of == r)
+        local = np.full(n, -1, np.int64)
+        local[mine] = np.arange(len(mine))
+        p = parent[mine]
+        lp = np.where(p == _gpu.NO_PARENT, np.int64(_gpu.NO_PARENT), local[np.where(p == _gpu.NO_PARENT, 0, p)])
+        out.append((mine, lp.astype(np.uint32)))
+    return out
+
+
 def exchange_counts(counts, group=None):
     """All-gather of this shard's per-view visible counts.  `counts`: 1-D int32 tensor (device tensor
     under NCCL).  Returns a [world_size, n_views] tensor on the same device."""

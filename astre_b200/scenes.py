@@ -80,6 +80,7 @@ class Scene:
     masks: np.ndarray = None   # [views_per_world]
     n_worlds: int = 1
     entities_per_world: int = 0
+    global_index: np.ndarray = None   # subtree shards: global entity index of every local slot
 
     @property
     def n(self):
@@ -90,7 +91,16 @@ class Scene:
         return len(self.masks)
 
     def shard(self, rank, world_size):
-        """Contiguous entity-range shard (flat scenes) or whole-world shard (batched worlds)."""
+        """Contiguous entity-range shard (flat scenes), whole-world shard (batched worlds) or
+        root-subtree shard (hierarchies; `.global_index` maps local slots back)."""
+        if self.parent is not None:
+            from . import multi
+            mine, local_parent = multi.shard_subtrees(self.parent, world_size)[rank]
+            sh = Scene(f"{self.name}[{rank}/{world_size}]", self.pos[mine], self.rot[mine], self.scale[mine],
+                       self.mesh[mine], self.shader[mine], self.flags[mine], local_parent, self.bounds, self.clip,
+                       self.masks, 1, self.entities_per_world)
+            sh.global_index = mine
+            return sh
         if self.n_worlds > 1:
             assert self.n_worlds % world_size == 0
             wl = self.n_worlds // world_size
@@ -98,7 +108,6 @@ class Scene:
             clip = self.clip[rank * wl:(rank + 1) * wl]
             n_worlds = wl
         else:
-            assert self.parent is None, "hierarchies shard by root subtree, not by range"
             per = -(-self.n // world_size)
             per = (per + 3) & ~3
             lo, hi = min(rank * per, self.n), min((rank + 1) * per, self.n)

@@ -65,6 +65,21 @@ def test_hierarchy_arbitrary_slot_order(oracle):
     check_scene(oracle, s)
 
 
+def test_hierarchy_subtree_shards(oracle):
+    """8e: a hierarchy sharded by root subtree -- every shard reproduces the unsharded world matrices of
+    its entities, and the shards' visible counts add up."""
+    s = scenes.config2(200_000, levels=8)
+    full_world, _, full_counts = oracle.frame(s)
+    total = 0
+    for r in range(3):
+        sh = s.shard(r, 3)
+        check_scene(oracle, sh)
+        world, counts, _, _ = run_scene(sh)
+        assert np.array_equal(oracle_lib.bits(world), oracle_lib.bits(full_world[sh.global_index]))
+        total += int(counts.sum())
+    assert total == int(full_counts.sum())
+
+
 def test_config3_five_views_1m(oracle):
     assert check_scene(oracle, scenes.config3(1 << 20)) > 0
 

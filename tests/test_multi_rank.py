@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -115,3 +116,35 @@ def test_shard_helpers():
     a = torch.tensor([[3, 1], [2, 5], [0, 7]], dtype=torch.int32)
     off, tot = multi.segment_offsets(a, 2)
     assert tot.tolist() == [5, 13] and off.tolist() == [5, 5 + 6]
+
+
+def test_shard_subtrees_partition_properties():
+    """Every entity lands on exactly one rank, together with its whole ancestor chain; loads are balanced."""
+    from astre_b200 import scenes, multi
+    s = scenes.config2(40_000, levels=6)
+    parts = multi.shard_subtrees(s.parent, 3)
+    seen = np.concatenate([m for m, _ in parts])
+    assert np.array_equal(np.sort(seen), np.arange(s.n))
+    for mine, lp in parts:
+        glob_parent = s.parent[mine]
+        has = glob_parent != 0xFFFFFFFF
+        assert np.array_equal(mine[lp[has]], glob_parent[has])           # local parent is the same entity
+        assert (lp[~has] == 0xFFFFFFFF).all()
+    sizes = [len(m) for m, _ in parts]
+    biggest_subtree = 2 ** 6
+    assert max(sizes) - min(sizes) <= 2 * biggest_subtree
+    with pytest.raises(ValueError):
+        multi.shard_subtrees(np.array([1, 0], np.uint32), 2)             # cycle
+
+
+def test_subtree_shards_reproduce_the_unsharded_world_matrices(oracle):
+    from astre_b200 import scenes
+    s = scenes.config2(30_000, levels=8)
+    full_world, full_keys, full_counts = oracle.frame(s)
+    total = 0
+    for r in range(4):
+        sh = s.shard(r, 4)
+        w, k, c = oracle.frame(sh)
+        assert np.array_equal(oracle_lib.bits(w), oracle_lib.bits(full_world[sh.global_index]))
+        total += int(c.sum())
+    assert total == int(full_counts.sum())
