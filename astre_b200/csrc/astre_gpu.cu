@@ -1139,11 +1139,19 @@ int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint
         ctx->cap_merge_tiles = cap;
     }
     if (n_samples && out_count) {
-        k_merge_table<<<ceil_div(((uint64_t)n_samples + 1) * 8, 256), 256, 0, s>>>(L, ctx->d_splits, ctx->d_tile_start);
+        cudaLaunchAttribute pdl;
+        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+        cfg.gridDim = dim3(ceil_div(((uint64_t)n_samples + 1) * 8, 256)); cfg.blockDim = dim3(256);
+        CK(cudaLaunchKernelEx(&cfg, k_merge_table, L, ctx->d_splits, ctx->d_tile_start));
         CK_LAUNCH();
         const uint32_t span = (uint32_t)kMergeBatchKeys - (L.n_lists << kSampleShift);
-        k_merge_tiles<<<ceil_div(L.total, span), kMergeThreads, 0, s>>>(L, ctx->d_splits, ctx->d_tile_start, ctx->d_merged_keys,
-                                                                        ctx->d_merged_src, out_first, out_count);
+        cfg.gridDim = dim3(ceil_div(L.total, span)); cfg.blockDim = dim3(kMergeThreads);
+        const unsigned long long of = out_first, oc = out_count;
+        CK(cudaLaunchKernelEx(&cfg, k_merge_tiles, L, (const uint32_t *)ctx->d_splits, (const uint32_t *)ctx->d_tile_start,
+                              ctx->d_merged_keys, ctx->d_merged_src, of, oc));
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ctx->ev_merge1, s));

@@ -86,6 +86,7 @@ k_merge_cuts(const __grid_constant__ MergeLists L, uint32_t t_first, uint32_t *_
 __global__ void __launch_bounds__(256)
 k_merge_table(const __grid_constant__ MergeLists L, uint32_t *__restrict__ splits, uint32_t *__restrict__ tile_start)
 {
+    cudaGridDependencySynchronize();                           // launched while the cut kernel drains
     const uint32_t n_samples = L.sample_base[L.n_lists];
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t m = gid >> 3, t = gid & 7u;                 // 8 lanes per sample; no early exit (shuffles below)
@@ -146,6 +147,7 @@ k_merge_tiles(const __grid_constant__ MergeLists L, const uint32_t *__restrict__
     const uint32_t G = L.n_lists;
     const uint32_t n_tiles = L.sample_base[G];
     const uint32_t span = kMergeBatchKeys - (G << kSampleShift);
+    cudaGridDependencySynchronize();                           // launched while k_merge_table drains
     // warps 0 and 1: first tile of this batch and of the next one
     if (warp < 2) {
         const unsigned long long target = (unsigned long long)(blockIdx.x + warp) * span;
