@@ -92,7 +92,7 @@ struct astre_gpu_ctx {
     std::vector<void *> imports;
     cudaEvent_t ev_merge0 = nullptr, ev_merge1 = nullptr;
     cudaStream_t merge_stream = nullptr;
-    bool merge_done = false;
+    bool merge_done = false, merge_begun = false;    // merge_begun: ev_merge0 recorded by astre_gpu_merge_prepare, tail still to come
 
     // staging for uploads
     unsigned char *d_stage = nullptr;    // two staging halves of stage_entities * 64 bytes
@@ -1158,6 +1158,7 @@ int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint
     ctx->n_merged = out_count;
     ctx->merge_stream = s;
     ctx->merge_done = true;
+    ctx->merge_begun = false;
     return ASTRE_OK;
 }
 
@@ -1168,6 +1169,7 @@ int merge_begin(astre_gpu_ctx *ctx, cudaStream_t s)
         CK(cudaEventCreate(&ctx->ev_merge1));
     }
     CK(cudaEventRecord(ctx->ev_merge0, s));
+    ctx->merge_begun = true;
     return ASTRE_OK;
 }
 
@@ -1316,7 +1318,7 @@ int astre_gpu_merge_published(astre_gpu_ctx *ctx, uint32_t n_lists, const void *
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (!ctx->ev_merge0) { if (int rc = merge_begin(ctx, s)) return rc; }
+    if (!ctx->merge_begun) { if (int rc = merge_begin(ctx, s)) return rc; }     // no prepare on this context this frame
     return merge_tail(ctx, L, out_first, out_count, s);
 }
 
