@@ -482,10 +482,10 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     __syncthreads();
     if (CULL && !WORLDS && threadIdx.x < F && s_counts[threadIdx.x])
         atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
-    if (CULL) {   // this CTA's region of the partial histograms (launches of one frame are stream-ordered)
-        uint32_t *region = P.block_hist + (size_t)blockIdx.x * kHistWords;
+    if (CULL) {   // into one of the partial histograms (RED: several CTAs share a region)
+        uint32_t *region = P.block_hist + (size_t)(blockIdx.x % P.hist_regions) * kHistWords;
         for (uint32_t i = threadIdx.x; i < plan.n_passes * 256u; i += kBlockThreads)
-            if (s_hist[i]) region[i] += s_hist[i];
+            if (s_hist[i]) atomicAdd(&region[i], s_hist[i]);
     }
 }
 

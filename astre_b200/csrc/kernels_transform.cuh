@@ -77,7 +77,8 @@ struct FrameParams {
     unsigned long long *keys;
     uint32_t *counts;              // [n_worlds*views_per_world]
     FrameControl *ctl;
-    uint32_t *block_hist;          // [regions][8][256] per-CTA digit histograms for the sort
+    uint32_t *block_hist;          // [hist_regions][8][256] partial digit histograms for the sort
+    uint32_t hist_regions;         // CTA b adds into region b % hist_regions
     unsigned long long key_cap;
     uint32_t n_meshes;
     uint32_t views_per_world;      // 0 = no culling
