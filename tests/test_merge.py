@@ -173,3 +173,31 @@ def test_multi_gpu_merge():
            "--master-port", "29631", os.path.join(here, "merge_worker.py"), "400000"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "MERGE_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _merge_kat():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "merge_kat_hand_derived.json")) as f:
+        d = json.load(f)
+    lists = [np.array([int(x, 16) for x in l], np.uint64) for l in d["lists"]]
+    return lists, np.array([int(x, 16) for x in d["keys"]], np.uint64), np.array(d["sources"], np.uint8)
+
+
+def test_oracle_merge_hand_derived_vector(oracle):
+    lists, keys, src = _merge_kat()
+    k, s = oracle.merge_lists(lists, SLOT_BITS)
+    assert np.array_equal(k, keys) and np.array_equal(s, src)
+
+
+@pytest.mark.gpu
+def test_gpu_merge_hand_derived_vector():
+    """The CUDA merge against the hand-derived vector (no oracle involved)."""
+    import torch
+    from astre_b200 import GpuContext
+    lists, keys, src = _merge_kat()
+    dev = [torch.from_numpy(l.view(np.int64)).cuda() for l in lists]
+    with GpuContext(1024, max_views=1) as ctx:
+        ctx.merge_lists([t.data_ptr() if t.numel() else None for t in dev], [len(l) for l in lists])
+        k, s = ctx.read_merged(0, len(keys))
+    assert np.array_equal(k, keys) and np.array_equal(s, src)
