@@ -108,12 +108,15 @@ class GlobalDrawList:
         self._gathered = None
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
         if mode == "p2p" and self.world > 1:
-            mine = [ctx.export_handle(0), ctx.export_handle(1)]
+            mine = [self.max_keys, ctx.export_handle(0), ctx.export_handle(1)]
             handles = [None] * self.world
             dist.all_gather_object(handles, mine, group=group)
+            if any(h[0] != self.max_keys for h in handles):
+                # the publish buffer layout (keys | samples | cut table) is derived from max_keys on every rank
+                raise ValueError(f"peer-to-peer merge needs the same max_keys on every rank, got {[h[0] for h in handles]}")
             for r in range(self.world):
                 if r != self.rank:
-                    self.peer[r] = [ctx.import_handle(handles[r][0]), ctx.import_handle(handles[r][1])]
+                    self.peer[r] = [ctx.import_handle(handles[r][1]), ctx.import_handle(handles[r][2])]
 
     def build(self, frame_index, sliced=False, stream=None):
         """Call after ctx.frame().  Returns (all_counts [G, F] on the host, out_first, out_count): the

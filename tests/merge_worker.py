@@ -26,7 +26,7 @@ def main():
     o_keys, o_src = oracle.merge_lists(lists, 26)
 
     shard = scene.shard(rank, world)
-    max_keys = shard.n * scene.views_per_world
+    max_keys = scene.shard(0, world).n * scene.views_per_world      # the same on every rank (publish buffer layout)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     with GpuContext(shard.n, max_views=scene.views_per_world, max_keys=max_keys, device=local) as ctx:
