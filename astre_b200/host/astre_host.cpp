@@ -211,6 +211,45 @@ std::vector<Mat4> calculateLightSpaceMatrices(const Frame &f)
     return out;
 }
 
+void GpuFrameInterpolator::snapshot()
+{
+    check(_ctx, astre_gpu_snapshot_trs(_ctx, nullptr), "astre_gpu_snapshot_trs");
+}
+
+static float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }   // glm::mix
+
+Frame GpuFrameInterpolator::interpolateFrame(const Frame &a, const Frame &b, float alpha)
+{
+    alpha = alpha < 0.0f ? 0.0f : (alpha > 1.0f ? 1.0f : alpha);                  // render.cpp:10
+    Frame result = b;                                                              // proxies, lights, lists of b (:22,41,66)
+    result.camera_position = Vec3{mixf(a.camera_position.x, b.camera_position.x, alpha),
+                                  mixf(a.camera_position.y, b.camera_position.y, alpha),
+                                  mixf(a.camera_position.z, b.camera_position.z, alpha)};
+    for (int i = 0; i < 16; ++i) {                                                 // math::interpolate, math.hpp:124-135
+        result.view_matrix[i] = mixf(a.view_matrix[i], b.view_matrix[i], alpha);
+        result.proj_matrix[i] = mixf(a.proj_matrix[i], b.proj_matrix[i], alpha);
+    }
+    check(_ctx, astre_gpu_interpolate(_ctx, alpha, nullptr), "astre_gpu_interpolate");
+    const std::uint32_t n = _mirror.slotCount();
+    std::vector<float> world(16 * (std::size_t)n);
+    if (n) check(_ctx, astre_gpu_read_world(_ctx, 0, n, world.data()), "astre_gpu_read_world");
+    for (auto &[id, proxy] : result.render_proxies) {
+        if (a.render_proxies.find(id) == a.render_proxies.end()) continue;        // :28-29
+        if (!_mirror.contains((Entity)id)) continue;
+        std::memcpy(proxy.uModel.data(), &world[16 * (std::size_t)_mirror.slotOf((Entity)id)], 64);
+    }
+    for (auto &[id, light] : result.gpu_lights) {                                 // :45-62, the fields this glue carries
+        auto it = a.gpu_lights.find(id);
+        if (it == a.gpu_lights.end()) continue;
+        const GPULight &la = it->second, &lb = b.gpu_lights.at(id);
+        light.position = Vec4{mixf(la.position.x, lb.position.x, alpha), mixf(la.position.y, lb.position.y, alpha),
+                              mixf(la.position.z, lb.position.z, alpha), mixf(la.position.w, lb.position.w, alpha)};
+        light.direction = Vec4{mixf(la.direction.x, lb.direction.x, alpha), mixf(la.direction.y, lb.direction.y, alpha),
+                               mixf(la.direction.z, lb.direction.z, alpha), lb.direction.w};
+    }
+    return result;
+}
+
 void GpuVisualSystem::run(float, Frame &frame)
 {
     frame.render_proxies.clear();                                            // visual_system.cpp:16

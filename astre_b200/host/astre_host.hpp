@@ -18,6 +18,8 @@
 //     (ECS/src/system/light_system.cpp:105-160)
 //   render::RenderProxy / render::Frame                             astre::gpu::RenderProxy / Frame
 //     (Render/include/render/render.hpp:45-86)
+//   render::interpolateFrame(const Frame&, const Frame&, float)     GpuFrameInterpolator::interpolateFrame
+//     (Render/src/render.cpp:8-68)
 //   EntityLoader::load / Registry::destroyEntity                    EntityMirror::spawn / despawn
 //     (Loader/src/entity_loader.cpp:11-76, ECS/src/registry.cpp:52-57)
 //   LuaBinding<TransformComponent> setters                          EntityMirror::setPosition/Rotation/Scale
@@ -179,6 +181,21 @@ private:
 
 // light_system.cpp:105-160
 std::vector<Mat4> calculateLightSpaceMatrices(const Frame &interpolated_frame);
+
+// render::interpolateFrame (Render/src/render.cpp:8-68).  The per-proxy part (:22-39) -- uModel =
+// translate(mix(p)) * toMat4(slerp(q)) * scale(mix(s)) for every proxy present in both frames -- runs on the
+// device for all entities at once: snapshot() at the end of logic tick `a` keeps that tick's TRS,
+// interpolateFrame() evaluates the mix between it and the current TRS (tick `b`).  Camera position and the
+// view / projection matrices are mixed on the host like the reference does (:16-20).
+class GpuFrameInterpolator {
+public:
+    GpuFrameInterpolator(EntityMirror &mirror, astre_gpu_ctx *ctx) : _mirror(mirror), _ctx(ctx) {}
+    void snapshot();                                                     // astre_gpu_snapshot_trs
+    Frame interpolateFrame(const Frame &a, const Frame &b, float alpha);
+private:
+    EntityMirror &_mirror;
+    astre_gpu_ctx *_ctx;
+};
 
 class GpuVisualSystem {
 public:

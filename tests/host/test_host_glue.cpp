@@ -24,6 +24,8 @@ void orc_camera_view_proj(const float *pos, const float *fwd, const float *up, f
 int orc_light_space(const float *pos3, const float *dir3, int type, float outer_cutoff, float *out16);
 void orc_mat4_mul(const float *a, const float *b, float *out);
 void orc_extract_view(const float *clip16, uint32_t phase_mask, orc_view *v);
+void orc_interpolate_trs(uint32_t n, float alpha, const float *pos_a, const float *rot_a, const float *scl_a,
+                         const float *pos_b, const float *rot_b, const float *scl_b, float *world16);
 uint64_t orc_frame(uint32_t n, const float *pos3, const float *rot4, const float *scl3, const uint32_t *parent,
                    const uint32_t *mesh_id, const uint32_t *shader_id, const uint8_t *flags, const orc_bounds *bounds,
                    uint32_t n_meshes, uint32_t n_worlds, uint32_t epw, uint32_t vpw, const orc_view *views, float *world16,
@@ -269,6 +271,71 @@ static void test_random_world(uint32_t n)
     check_against_oracle(w, frame);
 }
 
+// f1: GpuFrameInterpolator::interpolateFrame against render::interpolateFrame's per-proxy arithmetic (oracle).
+static void test_frame_interpolation(uint32_t n)
+{
+    World w(n + 8);
+    GpuFrameInterpolator interp(w.mirror, w.ctx);
+    std::mt19937 rng(7);
+    std::uniform_real_distribution<float> P(-40.0f, 40.0f), Q(-1.0f, 1.0f), S(0.5f, 2.0f);
+    auto unit_quat = [&]() { Quat q{Q(rng), Q(rng), Q(rng), Q(rng)}; const float l = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w); return Quat{q.x / l, q.y / l, q.z / l, q.w / l}; };
+    for (uint32_t i = 0; i < n; ++i) {
+        TransformComponent t;
+        t.position = Vec3{P(rng), P(rng) * 0.2f, P(rng) - 45.0f};
+        t.rotation = unit_quat();
+        t.scale = Vec3{S(rng), S(rng), S(rng)};
+        VisualComponent v; v.vertex_buffer_name = "cube_prefab"; v.shader_name = "deferred_shader"; v.visible = true;
+        w.mirror.spawn(2000 + i, t, &v, &w.names);
+    }
+    TransformComponent cam; cam.position = Vec3{0, 5, 15};
+    w.mirror.spawn(5, cam, nullptr, nullptr);
+    w.cameras.active_camera_entity = 5;
+    Frame fa, fb;
+    w.transforms.run(0.1f); w.cameras.run(0.1f, fa); w.visuals.run(0.1f, fa);
+    interp.snapshot();                                                   // tick a is what the renderer shows now
+    const uint32_t n_a = w.mirror.slotCount();
+    std::vector<float> pa(w.mirror.position(0), w.mirror.position(0) + 3 * n_a), ra(w.mirror.rotation(0), w.mirror.rotation(0) + 4 * n_a),
+        sa(w.mirror.scale(0), w.mirror.scale(0) + 3 * n_a);
+    for (uint32_t i = 0; i < n; i += 2) w.mirror.setPosition(2000 + i, Vec3{P(rng), 1.0f, P(rng) - 45.0f});
+    for (uint32_t i = 0; i < n; i += 3) w.mirror.setRotation(2000 + i, unit_quat());
+    for (uint32_t i = 0; i < n; i += 5) w.mirror.setScale(2000 + i, Vec3{S(rng), S(rng), S(rng)});
+    w.mirror.setPosition(5, Vec3{2, 6, 14});
+    TransformComponent late; late.position = Vec3{0, 0, -20};
+    VisualComponent lv; lv.vertex_buffer_name = "cube_prefab"; lv.shader_name = "deferred_shader"; lv.visible = true;
+    w.mirror.spawn(9000, late, &lv, &w.names);                           // exists in b only
+    w.transforms.run(0.1f); w.cameras.run(0.1f, fb); w.visuals.run(0.1f, fb);
+    const float alpha = 0.25f;
+    Frame r = interp.interpolateFrame(fa, fb, alpha);
+    const uint32_t n_b = w.mirror.slotCount();
+    std::vector<float> pa2(3 * n_b), ra2(4 * n_b), sa2(3 * n_b), exp(16 * (size_t)n_b);
+    std::copy(w.mirror.position(0), w.mirror.position(0) + 3 * n_b, pa2.begin());   // slots new in b: a := b
+    std::copy(w.mirror.rotation(0), w.mirror.rotation(0) + 4 * n_b, ra2.begin());
+    std::copy(w.mirror.scale(0), w.mirror.scale(0) + 3 * n_b, sa2.begin());
+    std::copy(pa.begin(), pa.end(), pa2.begin()); std::copy(ra.begin(), ra.end(), ra2.begin()); std::copy(sa.begin(), sa.end(), sa2.begin());
+    orc_interpolate_trs(n_b, alpha, pa2.data(), ra2.data(), sa2.data(), w.mirror.position(0), w.mirror.rotation(0), w.mirror.scale(0), exp.data());
+    EXPECT(r.render_proxies.size() == fb.render_proxies.size());
+    size_t both = 0, exact_t = 0, close_r = 0;
+    for (const auto &[id, proxy] : r.render_proxies) {
+        if (!fa.render_proxies.count(id)) {                              // render.cpp:28-29: keeps b's matrix
+            EXPECT(same_bits(proxy.uModel.data(), fb.render_proxies.at(id).uModel.data(), 16));
+            continue;
+        }
+        ++both;
+        const float *e = &exp[16 * (size_t)w.mirror.slotOf((Entity)id)];
+        exact_t += same_bits(proxy.uModel.data() + 12, e + 12, 4);       // translation column: mix only
+        bool ok = true;
+        for (int i = 0; i < 12; ++i) ok = ok && std::fabs(proxy.uModel[i] - e[i]) <= 2e-5f * (1.0f + std::fabs(e[i]));   // acosf/sinf: glibc vs CUDA
+        close_r += ok;
+    }
+    EXPECT(both > n / 50);
+    EXPECT(exact_t == both);
+    EXPECT(close_r == both);
+    EXPECT(fb.render_proxies.count(9000) == 1 && fa.render_proxies.count(9000) == 0);
+    const float cx = fa.camera_position.x * (1.0f - alpha) + fb.camera_position.x * alpha;
+    EXPECT(r.camera_position.x == cx);
+    EXPECT(r.view_matrix[12] == fa.view_matrix[12] * (1.0f - alpha) + fb.view_matrix[12] * alpha);
+}
+
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::string(argv[1]) == "--cpu";
@@ -276,6 +343,7 @@ int main(int argc, char **argv)
     if (!cpu_only) {
         test_level0_like_world();
         test_random_world(20000);
+        test_frame_interpolation(5000);
     }
     std::printf("%s: %d checks, %d failures%s\n", g_failures ? "FAILED" : "PASSED", g_checks, g_failures, cpu_only ? " (cpu-only subset)" : "");
     return g_failures ? 1 : 0;
