@@ -298,6 +298,21 @@ void GpuVisualSystem::run(float, Frame &frame)
             p.scale = Vec3{S[0], S[1], S[2]};
         }
     }
+
+    // f2: runs of one (view, shader, mesh) in the sorted list
+    frame.draw_runs.clear();
+    std::uint32_t n_runs = 0;
+    check(_ctx, astre_gpu_read_runs(_ctx, nullptr, 0, &n_runs), "astre_gpu_read_runs");
+    std::vector<astre_draw_run> runs(n_runs);
+    if (n_runs) check(_ctx, astre_gpu_read_runs(_ctx, runs.data(), n_runs, &n_runs), "astre_gpu_read_runs");
+    std::vector<std::uint64_t> view_first(n_views + 1, 0);
+    for (std::uint32_t v = 0; v < n_views; ++v) view_first[v + 1] = view_first[v] + counts[v];
+    frame.draw_runs.reserve(n_runs);
+    for (const astre_draw_run &r : runs) {
+        const std::uint32_t v = r.world_view & 31u;
+        frame.draw_runs.push_back(Frame::DrawRun{v, (std::uint32_t)(r.first - view_first[v]), r.count,
+                                                 (std::size_t)(r.shader_mesh >> 11), (std::size_t)(r.shader_mesh & 2047u)});
+    }
 }
 
 }  // namespace astre::gpu

@@ -104,6 +104,10 @@ struct Frame {
     std::uint32_t shadow_casters_count = 0;
     // view 0 = camera (Opaque), views 1.. = shadow casters (ShadowCaster): entity ids in draw order
     std::vector<std::vector<Entity>> draw_lists;
+    // f2: the lists cut into runs of one (view, shader, mesh): one instanced draw each instead of one
+    // glDrawElements per proxy and pass (Pipeline/src/deferred_shading.cpp:115-174).  `first` indexes draw_lists[view].
+    struct DrawRun { std::uint32_t view, first, count; std::size_t shader, vertex_buffer; };
+    std::vector<DrawRun> draw_runs;
 };
 
 // Dense slot <-> entity table with spawn/despawn and a dirty set: what keeps

@@ -155,6 +155,23 @@ static void check_against_oracle(World &w, Frame &frame)
     EXPECT(models_ok);
 }
 
+// f2: the runs tile every draw list exactly and are homogeneous in (shader, mesh)
+static void check_draw_runs(World &w, const Frame &frame)
+{
+    std::vector<size_t> covered(frame.draw_lists.size(), 0);
+    for (const Frame::DrawRun &r : frame.draw_runs) {
+        EXPECT(r.view < frame.draw_lists.size());
+        EXPECT(r.first == covered[r.view]);                          // runs come in list order, no gaps
+        EXPECT(r.count > 0 && r.first + r.count <= frame.draw_lists[r.view].size());
+        for (uint32_t i = 0; i < r.count; ++i) {
+            const uint32_t slot = w.mirror.slotOf(frame.draw_lists[r.view][r.first + i]);
+            if (w.mirror.shader(slot) != r.shader || w.mirror.mesh(slot) != r.vertex_buffer) { EXPECT(false); break; }
+        }
+        covered[r.view] += r.count;
+    }
+    for (size_t v = 0; v < frame.draw_lists.size(); ++v) EXPECT(covered[v] == frame.draw_lists[v].size());
+}
+
 static void test_level0_like_world()
 {
     World w(64);
@@ -264,6 +281,8 @@ static void test_random_world(uint32_t n)
     w.visuals.run(0.1f, frame);
     EXPECT(frame.draw_lists[0].size() > n / 50);
     check_against_oracle(w, frame);
+    check_draw_runs(w, frame);
+    EXPECT(frame.draw_runs.size() >= 4 && frame.draw_runs.size() < frame.draw_lists[0].size());
     for (uint32_t i = 0; i < n; i += 17) w.mirror.setPosition(1000 + i, Vec3{P(rng), 1.0f, P(rng) - 50.0f});
     for (uint32_t i = 0; i < n; i += 29) w.mirror.despawn(1000 + i);
     w.transforms.run(0.1f);
