@@ -92,6 +92,9 @@ struct astre_gpu_ctx {
     std::vector<void *> imports;
     cudaEvent_t ev_merge0 = nullptr, ev_merge1 = nullptr;
     cudaStream_t merge_stream = nullptr;
+    MergeDims *d_mdims = nullptr;                            // sizes of the merge when they are only known on the device
+    bool merge_dev = false;                                  // last merge used device-side sizes
+    uint32_t merge_slice_rank = 0, merge_slice_world = 0;
     bool merge_done = false, merge_begun = false;    // merge_begun: ev_merge0 recorded by astre_gpu_merge_prepare, tail still to come
 
     // staging for uploads
@@ -457,7 +460,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
                      ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads, ctx->d_long_runs,
                      ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
-                     ctx->d_mcuts };
+                     ctx->d_mcuts, ctx->d_mdims };
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1 };
@@ -1107,28 +1110,35 @@ int fill_lists(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_lists, const uint64
     uint32_t n_samples = 0;
     for (uint32_t t = 0; t < n_lists; ++t) {
         if (counts[t] > (1ull << ASTRE_KEY_SLOT_BITS) * ASTRE_MAX_VIEWS) return fail(ctx, ASTRE_ERR_INVALID, "list %u: count out of range", t);
-        L.n[t] = (uint32_t)counts[t];
-        L.sample_base[t] = n_samples;
+        L.d.n[t] = (uint32_t)counts[t];
+        L.d.sample_base[t] = n_samples;
         n_samples += (uint32_t)((counts[t] + kSampleStep - 1) >> kSampleShift);
         total += counts[t];
     }
     if (total >= (1ull << 24) * kSampleStep) return fail(ctx, ASTRE_ERR_CAPACITY, "global list of %llu keys exceeds 2^31", (unsigned long long)total);
-    L.sample_base[n_lists] = n_samples;
-    L.total = total;
+    L.d.sample_base[n_lists] = n_samples;
+    L.d.n_lists = n_lists;
+    L.d.total = total;
     return ASTRE_OK;
 }
 
-// table + tiles, given lists, samples and cut tables
-int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint64_t out_count, cudaStream_t s)
+// table + tiles, given lists, samples and cut tables.  Host-side sizes (L.dev_dims == nullptr): out_first /
+// out_count select the window.  Device-side sizes: n_samples_cap bounds the sample count, the window is slice
+// slice_rank of slice_world (0 = whole list) and at most out_count keys.
+int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint64_t out_count, uint32_t slice_rank,
+               uint32_t slice_world, uint32_t n_samples_cap, cudaStream_t s)
 {
-    const uint32_t n_samples = L.sample_base[L.n_lists];
-    out_first = std::min<uint64_t>(out_first, L.total);
-    out_count = std::min<uint64_t>(out_count, L.total - out_first);
+    const bool dev = L.dev_dims != nullptr;
+    const uint32_t n_samples = dev ? n_samples_cap : L.d.sample_base[L.n_lists];
+    if (!dev) {
+        out_first = std::min<uint64_t>(out_first, L.d.total);
+        out_count = std::min<uint64_t>(out_count, L.d.total - out_first);
+    }
     if (ctx->cap_merged < out_count || !ctx->d_merged_keys) {
         if (ctx->d_merged_keys) CK(cudaFree(ctx->d_merged_keys));
         if (ctx->d_merged_src) CK(cudaFree(ctx->d_merged_src));
         ctx->d_merged_keys = nullptr; ctx->d_merged_src = nullptr; ctx->cap_merged = 0;
-        const uint64_t cap = std::max<uint64_t>(out_count + out_count / 4, 1024);
+        const uint64_t cap = std::max<uint64_t>(dev ? out_count : out_count + out_count / 4, 1024);
         CK(cudaMalloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_merged_src, cap));
         ctx->cap_merged = cap;
@@ -1137,7 +1147,7 @@ int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint
         if (ctx->d_splits) CK(cudaFree(ctx->d_splits));
         if (ctx->d_tile_start) CK(cudaFree(ctx->d_tile_start));
         ctx->d_splits = nullptr; ctx->d_tile_start = nullptr; ctx->cap_merge_tiles = 0;
-        const uint32_t cap = n_samples + n_samples / 4 + 64;
+        const uint32_t cap = dev ? n_samples + 1 : n_samples + n_samples / 4 + 64;
         CK(cudaMalloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
         ctx->cap_merge_tiles = cap;
@@ -1148,18 +1158,23 @@ int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint
         pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
         cudaLaunchConfig_t cfg{};
         cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
-        cfg.gridDim = dim3(ceil_div(((uint64_t)n_samples + 1) * 8, 256)); cfg.blockDim = dim3(256);
+        // sizes only known on the device: fixed grids, the kernels stride over the real counts
+        const uint32_t table_grid = dev ? (uint32_t)ctx->sm_count * 4u : ceil_div(((uint64_t)n_samples + 1) * 8, 256);
+        cfg.gridDim = dim3(table_grid); cfg.blockDim = dim3(256);
         CK(cudaLaunchKernelEx(&cfg, k_merge_table, L, ctx->d_splits, ctx->d_tile_start));
         CK_LAUNCH();
         const uint32_t span = (uint32_t)kMergeBatchKeys - (L.n_lists << kSampleShift);
-        cfg.gridDim = dim3(ceil_div(L.total, span)); cfg.blockDim = dim3(kMergeThreads);
+        const uint32_t tiles_grid = dev ? (uint32_t)ctx->sm_count * 6u : ceil_div(L.d.total, span);
+        cfg.gridDim = dim3(tiles_grid); cfg.blockDim = dim3(kMergeThreads);
         const unsigned long long of = out_first, oc = out_count;
         CK(cudaLaunchKernelEx(&cfg, k_merge_tiles, L, (const uint32_t *)ctx->d_splits, (const uint32_t *)ctx->d_tile_start,
-                              ctx->d_merged_keys, ctx->d_merged_src, of, oc));
+                              ctx->d_merged_keys, ctx->d_merged_src, of, oc, slice_rank, slice_world));
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ctx->ev_merge1, s));
     ctx->n_merged = out_count;
+    ctx->merge_dev = dev;
+    ctx->merge_slice_rank = slice_rank; ctx->merge_slice_world = slice_world;
     ctx->merge_stream = s;
     ctx->merge_done = true;
     ctx->merge_begun = false;
@@ -1250,7 +1265,7 @@ int astre_gpu_merge_lists(astre_gpu_ctx *ctx, uint32_t n_lists, const void *cons
     }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    const uint32_t n_samples = L.sample_base[n_lists];
+    const uint32_t n_samples = L.d.sample_base[n_lists];
     if (ctx->cap_msamples < n_samples || !ctx->d_mcuts) {
         if (ctx->d_mcuts) CK(cudaFree(ctx->d_mcuts));
         ctx->d_mcuts = nullptr; ctx->cap_msamples = 0;
@@ -1269,7 +1284,7 @@ int astre_gpu_merge_lists(astre_gpu_ctx *ctx, uint32_t n_lists, const void *cons
         k_merge_cuts<<<grid, 256, 0, s>>>(L, 0u, ctx->d_mcuts, (size_t)ctx->cap_msamples);
         CK_LAUNCH();
     }
-    return merge_tail(ctx, L, out_first, out_count, s);
+    return merge_tail(ctx, L, out_first, out_count, 0, 0, 0, s);
 }
 
 // Peer-to-peer flow, step 1 (after the counts exchange): rank `rank` ranks every sample of every
@@ -1293,7 +1308,7 @@ int astre_gpu_merge_prepare(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank,
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     if (int rc = merge_begin(ctx, s)) return rc;
-    const uint32_t n_samples = L.sample_base[n_lists];
+    const uint32_t n_samples = L.d.sample_base[n_lists];
     if (n_samples) {
         uint32_t *own_cuts = const_cast<uint32_t *>(L.cuts[rank]);
         k_merge_cuts<<<std::min<uint32_t>(ceil_div(n_samples, 256), (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(L, rank, own_cuts, 0);
@@ -1323,19 +1338,104 @@ int astre_gpu_merge_published(astre_gpu_ctx *ctx, uint32_t n_lists, const void *
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     if (!ctx->merge_begun) { if (int rc = merge_begin(ctx, s)) return rc; }     // no prepare on this context this frame
-    return merge_tail(ctx, L, out_first, out_count, s);
+    return merge_tail(ctx, L, out_first, out_count, 0, 0, 0, s);
+}
+
+// Same two steps with the key counts left on the device: all_counts_dev is the all-gathered [n_lists][n_views]
+// table of per-view visible counts (uint32, device memory), exactly what the 8e exchange produces.  Nothing
+// here waits for the host, so the whole frame -> publish -> exchange -> merge chain can be enqueued ahead.
+static int lists_from_publish(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_lists, const void *const *publish)
+{
+    if (n_lists == 0 || n_lists > (uint32_t)kMaxLists) return fail(ctx, ASTRE_ERR_INVALID, "n_lists must be in 1..%d", kMaxLists);
+    if (ctx->world_bits) return fail(ctx, ASTRE_ERR_STATE, "batched worlds shard by whole worlds: their global list is the rank-major concatenation, no merge");
+    if ((uint64_t)n_lists * ctx->max_keys >= (1ull << 31)) return fail(ctx, ASTRE_ERR_CAPACITY, "n_lists * max_keys must stay below 2^31 for a merge with device-side counts");
+    const PublishLayout P = publish_layout(ctx->max_keys);
+    L = MergeLists{};
+    L.n_lists = n_lists;
+    L.slot_bits = ASTRE_KEY_SLOT_BITS;
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        if (!publish[t]) return fail(ctx, ASTRE_ERR_INVALID, "publish buffer %u is null", t);
+        const unsigned char *base = static_cast<const unsigned char *>(publish[t]);
+        L.keys[t] = reinterpret_cast<const unsigned long long *>(base);
+        L.samples[t] = reinterpret_cast<const unsigned long long *>(base + P.samples_off);
+        L.cuts[t] = reinterpret_cast<const uint32_t *>(base + P.cuts_off);
+    }
+    if (!ctx->d_mdims) CK(cudaMalloc(&ctx->d_mdims, sizeof(MergeDims)));
+    L.dev_dims = ctx->d_mdims;
+    return ASTRE_OK;
+}
+
+int astre_gpu_merge_prepare_dev(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish,
+                                const uint32_t *all_counts_dev, uint32_t n_views, void *stream)
+{
+    if (!ctx || !publish || !all_counts_dev || rank >= n_lists || n_views == 0) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    MergeLists L;
+    if (int rc = lists_from_publish(ctx, L, n_lists, publish)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (int rc = merge_begin(ctx, s)) return rc;
+    k_merge_dims<<<1, 32, 0, s>>>(all_counts_dev, n_lists, n_views, ctx->max_keys, ctx->d_mdims);
+    CK_LAUNCH();
+    uint32_t *own_cuts = const_cast<uint32_t *>(L.cuts[rank]);
+    k_merge_cuts<<<(uint32_t)ctx->sm_count * 8u, 256, 0, s>>>(L, rank, own_cuts, 0);
+    CK_LAUNCH();
+    return ASTRE_OK;
+}
+
+int astre_gpu_merge_published_dev(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish, uint32_t slice_rank,
+                                  uint32_t slice_world, uint64_t out_cap, void *stream)
+{
+    if (!ctx || !publish || (slice_world && slice_rank >= slice_world)) return ASTRE_ERR_INVALID;
+    if (!ctx->merge_begun || !ctx->d_mdims) return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_merge_published_dev needs astre_gpu_merge_prepare_dev on this context first");
+    CK(cudaSetDevice(ctx->device));
+    MergeLists L;
+    if (int rc = lists_from_publish(ctx, L, n_lists, publish)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint64_t whole = (uint64_t)n_lists * ctx->max_keys;
+    if (out_cap == 0) out_cap = slice_world ? (whole + slice_world - 1) / slice_world : whole;     // worst case
+    const uint32_t n_samples_cap = n_lists * publish_layout(ctx->max_keys).sample_cap;
+    return merge_tail(ctx, L, 0, out_cap, slice_rank, slice_world, n_samples_cap, s);
 }
 
 void *astre_gpu_device_merged_keys(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_keys : nullptr; }
 void *astre_gpu_device_merged_sources(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_src : nullptr; }
 
+// Number of keys the last merge kept (synchronises when the sizes were computed on the device).
+static int merged_count(astre_gpu_ctx *ctx, uint64_t *n_out)
+{
+    if (!ctx->merge_done) return fail(ctx, ASTRE_ERR_STATE, "no merge has been run");
+    if (ctx->merge_dev) {
+        CK(cudaStreamSynchronize(ctx->merge_stream));
+        MergeDims d;
+        CK(cudaMemcpy(&d, ctx->d_mdims, sizeof d, cudaMemcpyDeviceToHost));
+        uint64_t first = 0, count = d.total;
+        if (ctx->merge_slice_world) {
+            const uint64_t per = (d.total + ctx->merge_slice_world - 1) / ctx->merge_slice_world;
+            first = std::min<uint64_t>(per * ctx->merge_slice_rank, d.total);
+            count = std::min<uint64_t>(per, d.total - first);
+        }
+        *n_out = std::min<uint64_t>(count, ctx->n_merged);     // n_merged holds the capacity given to the merge
+    } else {
+        *n_out = ctx->n_merged;
+    }
+    return ASTRE_OK;
+}
+
+int astre_gpu_merged_count(astre_gpu_ctx *ctx, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return merged_count(ctx, n_out);
+}
+
 int astre_gpu_read_merged(astre_gpu_ctx *ctx, uint64_t first, uint64_t n, uint64_t *keys, uint8_t *sources)
 {
     if (!ctx) return ASTRE_ERR_INVALID;
-    if (!ctx->merge_done) return fail(ctx, ASTRE_ERR_STATE, "no merge has been run");
-    if (first + n > ctx->n_merged) return fail(ctx, ASTRE_ERR_INVALID, "range [%llu, %llu) exceeds the %llu merged keys",
-                                              (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)ctx->n_merged);
     CK(cudaSetDevice(ctx->device));
+    uint64_t have = 0;
+    if (int rc = merged_count(ctx, &have)) return rc;
+    if (first + n > have) return fail(ctx, ASTRE_ERR_INVALID, "range [%llu, %llu) exceeds the %llu merged keys",
+                                      (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)have);
     CK(cudaStreamSynchronize(ctx->merge_stream));
     if (n && keys) CK(cudaMemcpy(keys, ctx->d_merged_keys + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (n && sources) CK(cudaMemcpy(sources, ctx->d_merged_src + first, n, cudaMemcpyDeviceToHost));

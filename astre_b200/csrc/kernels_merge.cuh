@@ -38,16 +38,45 @@ constexpr int kSampleStep = 1 << kSampleShift;
 constexpr int kMergeWarps = 4;             // warps per CTA of k_merge_tiles
 constexpr int kMergeThreads = kMergeWarps * 32;
 
+struct MergeDims {                                  // sizes of one merge
+    uint32_t n[kMaxLists];                          // keys per list
+    uint32_t sample_base[kMaxLists + 1];            // first sample index of every list; [n_lists] = number of samples
+    uint32_t n_lists, pad;
+    unsigned long long total;
+};
+
 struct MergeLists {
     const unsigned long long *keys[kMaxLists];      // the lists
     const unsigned long long *samples[kMaxLists];   // sample j of list t = keys[t][j * 128] (see sample_stride_shift)
     const uint32_t *cuts[kMaxLists];                // cuts[t][m] = keys of list t preceding sample m
-    uint32_t n[kMaxLists];
-    uint32_t sample_base[kMaxLists + 1];            // first sample index of every list; [n_lists] = number of samples
+    MergeDims d;                                    // sizes known to the host ...
+    const MergeDims *dev_dims;                      // ... or, when not null, computed on the device (k_merge_dims)
     uint32_t n_lists, slot_bits;
     uint32_t sample_stride_shift, pad;              // samples[t][j << shift]: 0 = compact sample array, 7 = the list itself
-    unsigned long long total;
 };
+
+__device__ __forceinline__ const MergeDims &dims_of(const MergeLists &L) { return L.dev_dims ? *L.dev_dims : L.d; }
+
+// Sizes from the all-gathered per-view counts ([n_lists][n_views], as exchanged for 8e): no host round trip.
+__global__ void k_merge_dims(const uint32_t *__restrict__ counts, uint32_t n_lists, uint32_t n_views,
+                             unsigned long long max_keys, MergeDims *__restrict__ out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long total = 0;
+    uint32_t n_samples = 0;
+    for (uint32_t t = 0; t < n_lists; ++t) {
+        unsigned long long c = 0;
+        for (uint32_t v = 0; v < n_views; ++v) c += counts[(size_t)t * n_views + v];
+        if (c > max_keys) c = max_keys;                              // a rank that overflowed published max_keys keys
+        out->n[t] = (uint32_t)c;
+        out->sample_base[t] = n_samples;
+        n_samples += (uint32_t)((c + kSampleStep - 1) >> kSampleShift);
+        total += c;
+    }
+    out->sample_base[n_lists] = n_samples;
+    out->n_lists = n_lists;
+    out->total = total;
+}
 
 // Number of keys of `a[0..n)` whose class (key >> sb) is below `thr`.
 __device__ __forceinline__ uint32_t class_lower_bound(const unsigned long long *a, uint32_t n, uint32_t sb,
@@ -65,18 +94,20 @@ __device__ __forceinline__ uint32_t class_lower_bound(const unsigned long long *
 __global__ void __launch_bounds__(256)
 k_merge_cuts(const __grid_constant__ MergeLists L, uint32_t t_first, uint32_t *__restrict__ out, size_t out_stride)
 {
+    const MergeDims &D = dims_of(L);
     const uint32_t t = t_first + blockIdx.y;
-    const uint32_t n_samples = L.sample_base[L.n_lists];
+    const uint32_t n_samples = D.sample_base[L.n_lists];
     uint32_t *o = out + (size_t)blockIdx.y * out_stride;
     const unsigned long long *own = L.keys[t];
-    const uint32_t n_own = L.n[t];
+    const uint32_t n_own = D.n[t];
     for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n_samples; m += gridDim.x * blockDim.x) {
         uint32_t s = 0;
-        while (s + 1 < L.n_lists && m >= L.sample_base[s + 1]) ++s;
-        const uint32_t j = m - L.sample_base[s];
+        while (s + 1 < L.n_lists && m >= D.sample_base[s + 1]) ++s;
+        const uint32_t j = m - D.sample_base[s];
         uint32_t c;
         if (s == t) c = j << kSampleShift;
-        else c = class_lower_bound(own, n_own, L.slot_bits, (L.samples[s][(size_t)j << L.sample_stride_shift] >> L.slot_bits) + (t < s ? 1ull : 0ull));
+        else c = class_lower_bound(own, n_own, L.slot_bits,
+                                   (L.samples[s][(size_t)j << L.sample_stride_shift] >> L.slot_bits) + (t < s ? 1ull : 0ull));
         o[m] = c;
     }
 }
@@ -87,24 +118,27 @@ __global__ void __launch_bounds__(256)
 k_merge_table(const __grid_constant__ MergeLists L, uint32_t *__restrict__ splits, uint32_t *__restrict__ tile_start)
 {
     cudaGridDependencySynchronize();                           // launched while the cut kernel drains
-    const uint32_t n_samples = L.sample_base[L.n_lists];
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t m = gid >> 3, t = gid & 7u;                 // 8 lanes per sample; no early exit (shuffles below)
-    uint32_t c = 0;
-    if (t < L.n_lists) {
-        if (m < n_samples) c = L.cuts[t][m];
-        else if (m == n_samples) c = L.n[t];
-    }
-    uint32_t pos = c, q = (c + kSampleStep - 1) >> kSampleShift;
+    const MergeDims &D = dims_of(L);
+    const uint32_t n_samples = D.sample_base[L.n_lists];
+    const uint32_t n_items = (((n_samples + 1u) << 3) + 31u) & ~31u;          // 8 lanes per sample; whole warps iterate
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < n_items; gid += gridDim.x * blockDim.x) {
+        const uint32_t m = gid >> 3, t = gid & 7u;
+        uint32_t c = 0;
+        if (t < L.n_lists) {
+            if (m < n_samples) c = L.cuts[t][m];
+            else if (m == n_samples) c = D.n[t];
+        }
+        uint32_t pos = c, q = (c + kSampleStep - 1) >> kSampleShift;
 #pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-        pos += __shfl_xor_sync(0xffffffffu, pos, d);
-        q += __shfl_xor_sync(0xffffffffu, q, d);
-    }
-    if (m == n_samples) q = n_samples;
-    if (m <= n_samples) {
-        splits[(size_t)q * kMaxLists + t] = c;
-        if (t == 0) tile_start[q] = pos;
+        for (int d = 1; d < 8; d <<= 1) {
+            pos += __shfl_xor_sync(0xffffffffu, pos, d);
+            q += __shfl_xor_sync(0xffffffffu, q, d);
+        }
+        if (m == n_samples) q = n_samples;
+        if (m <= n_samples) {
+            splits[(size_t)q * kMaxLists + t] = c;
+            if (t == 0) tile_start[q] = pos;
+        }
     }
 }
 
@@ -135,99 +169,114 @@ __device__ __forceinline__ uint32_t warp_lower_bound(const uint32_t *__restrict_
 // equal class" keeps the (class, rank, slot) order.  Output positions are relative to out_first; batches
 // outside [out_first, out_first + out_count) are not loaded.  The final stores are contiguous.
 constexpr int kMergeBatchKeys = 2048;
+// slice_world == 0: keep [out_first, out_first + out_count).  slice_world > 0: keep slice `slice_rank` of
+// `slice_world` equal slices of the list (bounds computed here from the total, which may only be known on the
+// device), at most out_count keys.  Grid-stride over the batches (the grid may be smaller than their number).
 __global__ void __launch_bounds__(kMergeThreads)
 k_merge_tiles(const __grid_constant__ MergeLists L, const uint32_t *__restrict__ splits,
               const uint32_t *__restrict__ tile_start, unsigned long long *__restrict__ out_keys,
-              uint8_t *__restrict__ out_src, unsigned long long out_first, unsigned long long out_count)
+              uint8_t *__restrict__ out_src, unsigned long long out_first, unsigned long long out_count,
+              const uint32_t slice_rank, const uint32_t slice_world)
 {
     __shared__ unsigned long long s_keys[2][kMergeBatchKeys];
     __shared__ uint8_t s_tag[2][kMergeBatchKeys];
     __shared__ uint32_t s_run[2][kMaxLists + 2], s_lo[kMaxLists], s_q[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t G = L.n_lists;
-    const uint32_t n_tiles = L.sample_base[G];
     const uint32_t span = kMergeBatchKeys - (G << kSampleShift);
     cudaGridDependencySynchronize();                           // launched while k_merge_table drains
-    // warps 0 and 1: first tile of this batch and of the next one
-    if (warp < 2) {
-        const unsigned long long target = (unsigned long long)(blockIdx.x + warp) * span;
-        const uint32_t q = target >= L.total ? n_tiles : warp_lower_bound(tile_start, n_tiles, (uint32_t)target, lane);
-        if (lane == 0) s_q[warp] = q;
+    const MergeDims &D = dims_of(L);
+    const uint32_t n_tiles = D.sample_base[G];
+    const unsigned long long total_keys = D.total;
+    if (slice_world) {
+        const unsigned long long per = (total_keys + slice_world - 1) / slice_world;
+        out_first = min(per * slice_rank, total_keys);
+        out_count = min(min(per, total_keys - out_first), out_count);
     }
-    __syncthreads();
-    const uint32_t q0 = s_q[0], q1 = s_q[1];
-    if (q0 >= q1) return;
-    const unsigned long long t0 = tile_start[q0], t1 = tile_start[q1];
-    if (t1 <= out_first || t0 >= out_first + out_count) return;
-    if (tid < G) {
-        const uint32_t lo = splits[(size_t)q0 * kMaxLists + tid];
-        s_lo[tid] = lo;
-        s_run[1][tid] = splits[(size_t)q1 * kMaxLists + tid] - lo;      // run lengths, turned into offsets below
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t off = 0;
-        for (uint32_t t = 0; t < G; ++t) { s_run[0][t] = off; off += s_run[1][t]; }
-        s_run[0][G] = off;
-    }
-    __syncthreads();
-    const uint32_t total = s_run[0][G];
-    for (uint32_t t = 0; t < G; ++t) {
-        const uint32_t off_t = s_run[0][t], len_t = s_run[0][t + 1] - off_t;
-        const unsigned long long *src = L.keys[t] + s_lo[t];
-        for (uint32_t i = tid; i < len_t; i += kMergeThreads) { s_keys[0][off_t + i] = src[i]; s_tag[0][off_t + i] = (uint8_t)t; }
-    }
-    __syncthreads();
-    uint32_t cur = 0;
-    for (uint32_t R = G; R > 1; R = (R + 1) >> 1) {
-        const unsigned long long *src = s_keys[cur];
-        unsigned long long *dst = s_keys[cur ^ 1u];
-        const uint8_t *stag = s_tag[cur];
-        uint8_t *dtag = s_tag[cur ^ 1u];
-        const uint32_t *run = s_run[cur];
-        // Pair p = runs (2p, 2p+1) (the last pair may be a single run).  The output span of every pair is
-        // cut into chunks of K keys, one thread per chunk: K = ceil(total / (threads - P)) leaves room for
-        // the P partial chunks, so no thread crosses a pair boundary and control flow stays uniform.
-        const uint32_t P = (R + 1) >> 1;
-        const uint32_t K = max((total + (kMergeThreads - 1u - P)) / (kMergeThreads - P), 1u);
-        uint32_t a0 = 0, a1 = 0, b1 = 0, d = 0, next_chunk = 0;
-        bool have = false;
-        for (uint32_t pp = 0; pp < P; ++pp) {
-            const uint32_t r0 = run[2 * pp], r1 = run[min(2 * pp + 1, R)], r2 = run[min(2 * pp + 2, R)];
-            const uint32_t nch = (r2 - r0 + K - 1) / K;
-            if (!have && tid < next_chunk + nch) { have = true; a0 = r0; a1 = r1; b1 = r2; d = (tid - next_chunk) * K; }
-            next_chunk += nch;
+    const uint32_t n_batches = (uint32_t)((total_keys + span - 1) / span);
+    for (uint32_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+        __syncthreads();                                       // shared tables of the previous batch are free
+        // warps 0 and 1: first tile of this batch and of the next one
+        if (warp < 2) {
+            const unsigned long long target = (unsigned long long)(batch + warp) * span;
+            const uint32_t q = target >= total_keys ? n_tiles : warp_lower_bound(tile_start, n_tiles, (uint32_t)target, lane);
+            if (lane == 0) s_q[warp] = q;
         }
-        if (have) {
-            const uint32_t na = a1 - a0, nb = b1 - a1;
-            uint32_t slo = d > nb ? d - nb : 0u, shi = min(d, na);        // merge path: keys of the left run among the first d
-            while (slo < shi) {
-                const uint32_t mid = (slo + shi) >> 1;
-                if ((src[a0 + mid] >> ASTRE_KEY_SLOT_BITS) <= (src[a1 + d - 1 - mid] >> ASTRE_KEY_SLOT_BITS)) slo = mid + 1; else shi = mid;
-            }
-            uint32_t i = slo, j = d - slo, e = a0 + d;
-            const uint32_t end = min(e + K, b1);
-            unsigned long long ka = i < na ? src[a0 + i] : ~0ull, kb = j < nb ? src[a1 + j] : ~0ull;
-            for (uint32_t k = 0; k < K; ++k, ++e) {                         // branch-free two-way merge
-                const bool take = (ka >> ASTRE_KEY_SLOT_BITS) <= (kb >> ASTRE_KEY_SLOT_BITS);   // left run (lower ranks) first on equal class
-                const uint32_t idx = take ? a0 + i : a1 + j;
-                if (e < end) { dst[e] = take ? ka : kb; dtag[e] = stag[idx]; }
-                i += take ? 1u : 0u; j += take ? 0u : 1u;
-                const bool more = take ? i < na : j < nb;
-                const unsigned long long nk = more ? src[take ? a0 + i : a1 + j] : ~0ull;
-                if (take) ka = nk; else kb = nk;
-            }
-        }
-        // runs of the next round: run p = old runs 2p and 2p+1
-        if (tid <= P) s_run[cur ^ 1u][tid] = run[min(2 * tid, R)];
         __syncthreads();
-        cur ^= 1u;
-    }
-    for (uint32_t e = tid; e < total; e += kMergeThreads) {
-        const unsigned long long at = t0 + e;
-        if (at >= out_first && at - out_first < out_count) {
-            out_keys[at - out_first] = s_keys[cur][e];
-            out_src[at - out_first] = s_tag[cur][e];
+        const uint32_t q0 = s_q[0], q1 = s_q[1];
+        if (q0 >= q1) continue;
+        const unsigned long long t0 = tile_start[q0], t1 = tile_start[q1];
+        if (t1 <= out_first || t0 >= out_first + out_count) continue;
+        if (tid < G) {
+            const uint32_t lo = splits[(size_t)q0 * kMaxLists + tid];
+            s_lo[tid] = lo;
+            s_run[1][tid] = splits[(size_t)q1 * kMaxLists + tid] - lo;      // run lengths, turned into offsets below
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t off = 0;
+            for (uint32_t t = 0; t < G; ++t) { s_run[0][t] = off; off += s_run[1][t]; }
+            s_run[0][G] = off;
+        }
+        __syncthreads();
+        const uint32_t total = s_run[0][G];
+        for (uint32_t t = 0; t < G; ++t) {
+            const uint32_t off_t = s_run[0][t], len_t = s_run[0][t + 1] - off_t;
+            const unsigned long long *src = L.keys[t] + s_lo[t];
+            for (uint32_t i = tid; i < len_t; i += kMergeThreads) { s_keys[0][off_t + i] = src[i]; s_tag[0][off_t + i] = (uint8_t)t; }
+        }
+        __syncthreads();
+        uint32_t cur = 0;
+        for (uint32_t R = G; R > 1; R = (R + 1) >> 1) {
+            const unsigned long long *src = s_keys[cur];
+            unsigned long long *dst = s_keys[cur ^ 1u];
+            const uint8_t *stag = s_tag[cur];
+            uint8_t *dtag = s_tag[cur ^ 1u];
+            const uint32_t *run = s_run[cur];
+            // Pair p = runs (2p, 2p+1) (the last pair may be a single run).  The output span of every pair is
+            // cut into chunks of K keys, one thread per chunk: K = ceil(total / (threads - P)) leaves room for
+            // the P partial chunks, so no thread crosses a pair boundary and control flow stays uniform.
+            const uint32_t P = (R + 1) >> 1;
+            const uint32_t K = max((total + (kMergeThreads - 1u - P)) / (kMergeThreads - P), 1u);
+            uint32_t a0 = 0, a1 = 0, b1 = 0, d = 0, next_chunk = 0;
+            bool have = false;
+            for (uint32_t pp = 0; pp < P; ++pp) {
+                const uint32_t r0 = run[2 * pp], r1 = run[min(2 * pp + 1, R)], r2 = run[min(2 * pp + 2, R)];
+                const uint32_t nch = (r2 - r0 + K - 1) / K;
+                if (!have && tid < next_chunk + nch) { have = true; a0 = r0; a1 = r1; b1 = r2; d = (tid - next_chunk) * K; }
+                next_chunk += nch;
+            }
+            if (have) {
+                const uint32_t na = a1 - a0, nb = b1 - a1;
+                uint32_t slo = d > nb ? d - nb : 0u, shi = min(d, na);        // merge path: keys of the left run among the first d
+                while (slo < shi) {
+                    const uint32_t mid = (slo + shi) >> 1;
+                    if ((src[a0 + mid] >> ASTRE_KEY_SLOT_BITS) <= (src[a1 + d - 1 - mid] >> ASTRE_KEY_SLOT_BITS)) slo = mid + 1; else shi = mid;
+                }
+                uint32_t i = slo, j = d - slo, e = a0 + d;
+                const uint32_t end = min(e + K, b1);
+                unsigned long long ka = i < na ? src[a0 + i] : ~0ull, kb = j < nb ? src[a1 + j] : ~0ull;
+                for (uint32_t k = 0; k < K; ++k, ++e) {                         // branch-free two-way merge
+                    const bool take = (ka >> ASTRE_KEY_SLOT_BITS) <= (kb >> ASTRE_KEY_SLOT_BITS);   // left run (lower ranks) first on equal class
+                    const uint32_t idx = take ? a0 + i : a1 + j;
+                    if (e < end) { dst[e] = take ? ka : kb; dtag[e] = stag[idx]; }
+                    i += take ? 1u : 0u; j += take ? 0u : 1u;
+                    const bool more = take ? i < na : j < nb;
+                    const unsigned long long nk = more ? src[take ? a0 + i : a1 + j] : ~0ull;
+                    if (take) ka = nk; else kb = nk;
+                }
+            }
+            // runs of the next round: run p = old runs 2p and 2p+1
+            if (tid <= P) s_run[cur ^ 1u][tid] = run[min(2 * tid, R)];
+            __syncthreads();
+            cur ^= 1u;
+        }
+        for (uint32_t e = tid; e < total; e += kMergeThreads) {
+            const unsigned long long at = t0 + e;
+            if (at >= out_first && at - out_first < out_count) {
+                out_keys[at - out_first] = s_keys[cur][e];
+                out_src[at - out_first] = s_tag[cur][e];
+            }
         }
     }
 }

@@ -259,6 +259,24 @@ class GpuContext:
         oc = 0xFFFFFFFFFFFFFFFF if out_count is None else int(out_count)
         self._check(self._lib.astre_gpu_merge_published(self._h, g, ptrs, _ptr(cnt, C.c_uint64), int(out_first), oc, stream))
 
+    def merge_prepare_dev(self, rank, publish_ptrs, all_counts_dev_ptr, n_views, stream=None):
+        """Step 1 with the counts left on the device ([n_lists][n_views] uint32 table, e.g. the all-gathered tensor)."""
+        g = len(publish_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in publish_ptrs])
+        self._check(self._lib.astre_gpu_merge_prepare_dev(self._h, g, int(rank), ptrs, C.c_void_p(int(all_counts_dev_ptr)),
+                                                          int(n_views), stream))
+
+    def merge_published_dev(self, publish_ptrs, slice_rank=0, slice_world=0, out_cap=0, stream=None):
+        """Step 2 with device-side sizes: slice `slice_rank` of `slice_world` (0 = the whole list)."""
+        g = len(publish_ptrs)
+        ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in publish_ptrs])
+        self._check(self._lib.astre_gpu_merge_published_dev(self._h, g, ptrs, int(slice_rank), int(slice_world), int(out_cap), stream))
+
+    def merged_count(self):
+        n = C.c_uint64()
+        self._check(self._lib.astre_gpu_merged_count(self._h, C.byref(n)))
+        return n.value
+
     def read_merged(self, first, n):
         keys = np.empty(int(n), np.uint64)
         src = np.empty(int(n), np.uint8)

@@ -118,6 +118,20 @@ class GlobalDrawList:
                 if r != self.rank:
                     self.peer[r] = [ctx.import_handle(handles[r][1]), ctx.import_handle(handles[r][2])]
 
+    def build_enqueue(self, frame_index, sliced=False, out_cap=0, stream=None):
+        """Peer-to-peer flow with the key counts left on the device: nothing here waits for the GPU, so frames
+        and merges can be enqueued back to back.  The list is in the library's merge buffers afterwards
+        (ctx.merged_count() / ctx.read_merged synchronise)."""
+        assert self.mode == "p2p" or self.world == 1
+        parity = frame_index & 1
+        self.ctx.publish_keys(parity, stream)
+        self._all_counts = exchange_counts(self.counts_dev, self.group)          # [G, F] int32, stays on the device
+        ptrs = [self.peer[r][parity] for r in range(self.world)]
+        self.ctx.merge_prepare_dev(self.rank, ptrs, self._all_counts.data_ptr(), self.n_views, stream)
+        if self.world > 1:
+            dist.all_reduce(self._token, group=self.group)                       # device-side barrier
+        self.ctx.merge_published_dev(ptrs, self.rank if sliced else 0, self.world if sliced else 0, out_cap, stream)
+
     def build(self, frame_index, sliced=False, stream=None):
         """Call after ctx.frame().  Returns (all_counts [G, F] on the host, out_first, out_count): the
         merged keys / sources of positions [out_first, out_first + out_count) are in the library's

@@ -280,6 +280,19 @@ ASTRE_API int astre_gpu_merge_prepare(astre_gpu_ctx *ctx, uint32_t n_lists, uint
                                       const uint64_t *counts, void *stream);
 ASTRE_API int astre_gpu_merge_published(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish,
                                         const uint64_t *counts, uint64_t out_first, uint64_t out_count, void *stream);
+/* The same two steps with the key counts left on the device: all_counts_dev is
+ * the all-gathered [n_lists][n_views] table of per-view counts (uint32, device
+ * memory) -- what the 8e exchange produces.  Nothing waits for the host, so the
+ * frame -> publish -> exchange -> merge chain can be enqueued ahead.  The merge
+ * keeps slice slice_rank of slice_world equal slices of the list (slice_world 0:
+ * the whole list), at most out_cap keys (0: worst case from max_keys);
+ * n_lists * max_keys must stay below 2^31. */
+ASTRE_API int astre_gpu_merge_prepare_dev(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish,
+                                          const uint32_t *all_counts_dev, uint32_t n_views, void *stream);
+ASTRE_API int astre_gpu_merge_published_dev(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish,
+                                            uint32_t slice_rank, uint32_t slice_world, uint64_t out_cap, void *stream);
+/* Keys kept by the last merge (synchronises if the sizes were computed on the device). */
+ASTRE_API int astre_gpu_merged_count(astre_gpu_ctx *ctx, uint64_t *n_out);
 /* Result of the last merge: keys[i], sources[i] (= rank) for global position
  * out_first + i.  read_merged synchronises; `first` is relative to out_first. */
 ASTRE_API void *astre_gpu_device_merged_keys(astre_gpu_ctx *ctx);     /* uint64[] */

@@ -110,6 +110,25 @@ def test_gpu_merge_of_range_shards(oracle, n, g):
         last.merge_published(ptrs, counts, out_first=lo, out_count=hi - lo)
         k4, s4 = last.read_merged(0, hi - lo)
         assert np.array_equal(k4, o_keys[lo:hi]) and np.array_equal(s4, o_src[lo:hi])
+        # the same flow with the counts left on the device (the all-gathered [G, F] table of per-view counts)
+        import torch
+        table = torch.from_numpy(np.stack([c.read_counts() for c in ctxs]).astype(np.int32)).cuda()
+        for r in range(g):
+            ctxs[r].merge_prepare_dev(r, ptrs, table.data_ptr(), scene.views_per_world)
+            ctxs[r].sync()
+        last.merge_published_dev(ptrs)
+        assert last.merged_count() == total
+        k5, s5 = last.read_merged(0, total)
+        assert np.array_equal(k5, o_keys) and np.array_equal(s5, o_src)
+        per = -(-total // g)
+        for r in (0, g - 1):
+            ctxs[r].merge_prepare_dev(r, ptrs, table.data_ptr(), scene.views_per_world)
+            ctxs[r].merge_published_dev(ptrs, slice_rank=r, slice_world=g)
+            first = min(r * per, total)
+            cnt = min(per, total - first)
+            assert ctxs[r].merged_count() == cnt
+            k6, s6 = ctxs[r].read_merged(0, cnt)
+            assert np.array_equal(k6, o_keys[first:first + cnt]) and np.array_equal(s6, o_src[first:first + cnt])
     finally:
         for c in ctxs:
             c.close()

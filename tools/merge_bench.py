@@ -109,6 +109,26 @@ def distributed(args):
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
                 out[name + "_ordered"] = bool(ok.item())
                 out["keys_total"] = int(all_counts.sum())
+        # peer to peer with the key counts left on the device: no host round trip per frame
+        g = multi.GlobalDrawList(ctx, 5, max_keys, mode="p2p")
+        for sliced in (False, True):
+            def step():
+                ctx.frame()
+                g.build_enqueue(frame[0], sliced=sliced)
+                frame[0] += 1
+            name = f"p2p_dev{'_sliced' if sliced else ''}"
+            out[name + "_ms"] = timed(step)
+            out[name + "_merge_kernels_ms"] = ctx.last_merge_ms()
+            count = ctx.merged_count()
+            keys, src = merged_tensors(ctx, count, dev)
+            ok = torch.tensor([1 if check_order(keys, src) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            out[name + "_ordered"] = bool(ok.item())
+
+        def frame_no_sync():
+            ctx.frame()
+            multi.exchange_counts(counts_dev)
+        out["frame+counts_nosync_ms"] = timed(frame_no_sync)
         dist.barrier()
     if rank == 0:
         out.update({"mode": "distributed", "gpus": world, "entities_per_gpu": n})
