@@ -342,3 +342,72 @@ def test_sort_ties_long_runs(oracle, ties, monkeypatch):
     s.flags = gpu.make_flags(np.arange(n) % 16 != 15, np.full(n, 5, np.uint8))
     n_keys = check_scene(oracle, s)
     assert n_keys > 80_000
+
+
+def _random_scene(rng, i):
+    """A small adversarial scene: random size, view count, cameras (perspective, orthographic, degenerate),
+    masks, flags, optional parent forest, a sprinkle of special float values, random mesh bounds."""
+    n = int(rng.choice([1, 2, 31, 33, 127, 129, 500, 1025, 3000]))
+    s = scenes.config1(n)
+    s.name = f"fuzz-{i}"
+    s.pos = (rng.standard_normal((n, 3)) * rng.choice([0.1, 5.0, 80.0])).astype(np.float32)
+    s.pos[:, 2] -= np.float32(rng.choice([0.0, 20.0, 200.0]))
+    q = rng.standard_normal((n, 4)).astype(np.float32)
+    if rng.random() < 0.7:
+        q /= np.sqrt((q * q).sum(axis=1, keepdims=True, dtype=np.float32)) + np.float32(1e-20)
+    s.rot = q.astype(np.float32)
+    s.scale = np.exp(rng.standard_normal((n, 3))).astype(np.float32) * np.float32(rng.choice([1.0, 0.01, 50.0]))
+    if rng.random() < 0.5:
+        specials = np.array([0.0, -0.0, 1e-42, np.inf, -np.inf, np.nan, 3e38, -1.0, 0.5], np.float32)
+        for arr in (s.pos, s.rot, s.scale):
+            pick = rng.random(arr.shape) < 0.03
+            arr[pick] = specials[rng.integers(0, len(specials), pick.sum())]
+    n_meshes = int(rng.integers(1, 9))
+    s.bounds = scenes.PREFAB_BOUNDS[:n_meshes].copy()
+    s.bounds[:, 3:7] = np.abs(rng.standard_normal((n_meshes, 4))).astype(np.float32) * (rng.random((n_meshes, 4)) < 0.7)
+    s.mesh = rng.integers(0, n_meshes + (1 if rng.random() < 0.3 else 0), n).astype(np.uint32)    # sometimes out of range: never drawn
+    s.shader = rng.integers(0, int(rng.choice([1, 4, 256])), n).astype(np.uint32)
+    s.flags = gpu.make_flags(rng.random(n) < 0.9, rng.integers(0, 16, n).astype(np.uint8))
+    F = int(rng.integers(1, 9))
+    clips = []
+    for _ in range(F):
+        kind = rng.random()
+        eye = rng.standard_normal(3) * 10.0
+        fwd = rng.standard_normal(3)
+        fwd /= np.linalg.norm(fwd) + 1e-9
+        if kind < 0.5:
+            clips.append(gpu.camera_matrices(eye, fwd, (0.0, 1.0, 0.0), float(rng.uniform(20, 120)), float(rng.uniform(0.5, 2.5)),
+                                             float(rng.choice([0.01, 0.1, 1.0])), float(rng.choice([50.0, 1000.0, 1e5])))[2])
+        elif kind < 0.9:
+            h = float(rng.choice([5.0, 100.0, 2000.0]))
+            clips.append(gpu.ortho_view_matrix(eye, eye + fwd, (0.0, 1.0, 0.0), -h, h, -h, h, 0.1, float(rng.choice([100.0, 5000.0]))))
+        else:
+            clips.append((rng.standard_normal(16) * rng.choice([1.0, 0.0])).astype(np.float32))    # arbitrary / all-zero matrix
+    s.clip = np.stack(clips)[None].astype(np.float32)
+    s.masks = rng.integers(0, 16, F).astype(np.uint8)
+    if n > 4 and rng.random() < 0.4:                                       # random forest, parents anywhere (not slot-ordered)
+        depth_cap = int(rng.integers(1, 7))
+        parent = np.full(n, 0xFFFFFFFF, np.uint32)
+        depth = np.zeros(n, np.int64)
+        order = rng.permutation(n)
+        for k in range(1, n):
+            if rng.random() < 0.8:
+                p = order[rng.integers(0, k)]
+                if depth[p] < depth_cap:
+                    parent[order[k]] = p
+                    depth[order[k]] = depth[p] + 1
+        s.parent = parent
+    return s
+
+
+def test_fuzz_small_scenes(oracle):
+    """150 random small scenes (sizes around tile boundaries, 1..8 views of every kind including degenerate
+    matrices, random masks / flags / bounds / parents, special values): world matrices, counts and sorted keys
+    bit-exact against the oracle."""
+    rng = np.random.default_rng(20261019)
+    for i in range(150):
+        s = _random_scene(rng, i)
+        try:
+            check_scene(oracle, s)
+        except AssertionError as e:
+            raise AssertionError(f"scene {i} (n={s.n}, views={s.views_per_world}, hier={s.parent is not None}): {e}") from None
