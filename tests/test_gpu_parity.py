@@ -411,3 +411,36 @@ def test_fuzz_small_scenes(oracle):
             check_scene(oracle, s)
         except AssertionError as e:
             raise AssertionError(f"scene {i} (n={s.n}, views={s.views_per_world}, hier={s.parent is not None}): {e}") from None
+
+
+def test_fuzz_batched_worlds(oracle):
+    """Random batches of independent worlds: world sizes on and off the 128-entity warp tile (cached and
+    uncached view records), 1..3 views per world, random cameras per world."""
+    rng = np.random.default_rng(424242)
+    for i in range(40):
+        n_worlds = int(rng.choice([2, 3, 5, 16, 64]))
+        epw = int(rng.choice([4, 36, 128, 132, 256, 1000]))
+        F = int(rng.integers(1, 4))
+        n = n_worlds * epw
+        s = scenes.config1(n)
+        s.name = f"fuzz-worlds-{i}"
+        s.pos = (rng.standard_normal((n, 3)) * rng.choice([5.0, 60.0])).astype(np.float32)
+        s.scale = np.exp(rng.standard_normal((n, 3)) * 0.5).astype(np.float32)
+        s.flags = gpu.make_flags(rng.random(n) < 0.9, rng.integers(0, 16, n).astype(np.uint8))
+        clips = []
+        for _ in range(n_worlds * F):
+            eye = rng.standard_normal(3) * 20.0
+            fwd = rng.standard_normal(3)
+            fwd /= np.linalg.norm(fwd) + 1e-9
+            if rng.random() < 0.6:
+                clips.append(gpu.camera_matrices(eye, fwd, (0.0, 1.0, 0.0), float(rng.uniform(30, 110)), 1.7, 0.1, 1000.0)[2])
+            else:
+                h = float(rng.choice([20.0, 300.0]))
+                clips.append(gpu.ortho_view_matrix(eye, eye + fwd, (0.0, 1.0, 0.0), -h, h, -h, h, 0.1, 500.0))
+        s.clip = np.stack(clips).reshape(n_worlds, F, 16).astype(np.float32)
+        s.masks = rng.integers(1, 16, F).astype(np.uint8)
+        s.n_worlds, s.entities_per_world = n_worlds, epw
+        try:
+            check_scene(oracle, s)
+        except AssertionError as e:
+            raise AssertionError(f"scene {i} (worlds={n_worlds} x {epw}, views={F}): {e}") from None
