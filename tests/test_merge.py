@@ -220,3 +220,32 @@ def test_gpu_merge_hand_derived_vector():
         ctx.merge_lists([t.data_ptr() if t.numel() else None for t in dev], [len(l) for l in lists])
         k, s = ctx.read_merged(0, len(keys))
     assert np.array_equal(k, keys) and np.array_equal(s, src)
+
+
+@pytest.mark.gpu
+def test_gpu_merge_fuzz_random_lists(oracle):
+    """Synthetic lists straight into the merge: 1..8 lists, empty to 60k keys, from one class for everything
+    (ties across all lists over thousands of keys) to all-distinct classes, skewed sizes."""
+    import torch
+    from astre_b200 import GpuContext
+    rng = np.random.default_rng(99)
+    with GpuContext(1024, max_views=1) as ctx:
+        for i in range(60):
+            g = int(rng.integers(1, 9))
+            n_classes = int(rng.choice([1, 2, 17, 1000, 1 << 20]))
+            lists = []
+            for _ in range(g):
+                n = int(rng.choice([0, 1, 127, 128, 129, 5000, 60000])) if rng.random() < 0.7 else int(rng.integers(0, 60001))
+                cls = rng.integers(0, n_classes, n).astype(np.uint64)
+                slot = rng.choice(1 << 22, n, replace=False).astype(np.uint64)
+                lists.append(np.sort((cls << np.uint64(SLOT_BITS)) | slot))
+            o_keys, o_src = oracle.merge_lists(lists, SLOT_BITS)
+            dev = [torch.from_numpy(l.view(np.int64)).cuda() for l in lists]
+            ctx.merge_lists([t.data_ptr() if t.numel() else None for t in dev], [len(l) for l in lists])
+            k, s = ctx.read_merged(0, len(o_keys))
+            assert np.array_equal(k, o_keys) and np.array_equal(s, o_src), f"case {i}: g={g} classes={n_classes} sizes={[len(l) for l in lists]}"
+            if len(o_keys) > 10:
+                lo, hi = len(o_keys) // 4, len(o_keys) // 4 + len(o_keys) // 3
+                ctx.merge_lists([t.data_ptr() if t.numel() else None for t in dev], [len(l) for l in lists], out_first=lo, out_count=hi - lo)
+                k, s = ctx.read_merged(0, hi - lo)
+                assert np.array_equal(k, o_keys[lo:hi]) and np.array_equal(s, o_src[lo:hi]), f"case {i} (window)"
