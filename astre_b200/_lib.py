@@ -74,6 +74,8 @@ SIGNATURES = {
     "astre_gpu_merge_published": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), _U64, C.c_uint64, C.c_uint64, _P]),
     "astre_gpu_merge_prepare_dev": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P), _P, C.c_uint32, _P]),
     "astre_gpu_merge_published_dev": (C.c_int, [_P, C.c_uint32, C.POINTER(_P), C.c_uint32, C.c_uint32, C.c_uint64, _P]),
+    "astre_gpu_merge_p2p": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P), C.POINTER(_P), C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.c_uint64, _P]),
     "astre_gpu_merged_count": (C.c_int, [_P, _U64]),
     "astre_gpu_device_merged_keys": (_P, [_P]),
     "astre_gpu_device_merged_sources": (_P, [_P]),

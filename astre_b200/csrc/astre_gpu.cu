@@ -92,6 +92,8 @@ struct astre_gpu_ctx {
     std::vector<void *> imports;
     cudaEvent_t ev_merge0 = nullptr, ev_merge1 = nullptr;
     cudaStream_t merge_stream = nullptr;
+    uint32_t *d_merge_error = nullptr;                       // set by k_peer_sync when a peer never signalled
+    bool merge_p2p_flags = false;
     MergeDims *d_mdims = nullptr;                            // sizes of the merge when they are only known on the device
     bool merge_dev = false;                                  // last merge used device-side sizes
     uint32_t merge_slice_rank = 0, merge_slice_world = 0;
@@ -460,7 +462,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
                      ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads, ctx->d_long_runs,
                      ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
-                     ctx->d_mcuts, ctx->d_mdims };
+                     ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1 };
@@ -1077,16 +1079,17 @@ void *astre_gpu_device_sorted_keys(astre_gpu_ctx *ctx)
 
 namespace {
 
-// Publish buffer: keys[max_keys] | samples[max_keys/128 + 1] | cuts[kMaxLists * (max_keys/128 + 1)].
+// Publish buffer: keys[max_keys] | samples[max_keys/128 + 1] | cuts[kMaxLists * (max_keys/128 + 1)] | PublishHeader.
 // Every rank of a job uses the same max_keys, so every rank knows every peer's layout.
-struct PublishLayout { size_t samples_off, cuts_off, bytes; uint32_t sample_cap; };
+struct PublishLayout { size_t samples_off, cuts_off, header_off, bytes; uint32_t sample_cap; };
 PublishLayout publish_layout(uint64_t max_keys)
 {
     PublishLayout P;
     P.sample_cap = (uint32_t)(max_keys / kSampleStep + 1);
     P.samples_off = (std::max<uint64_t>(max_keys, 1) * 8 + 255) / 256 * 256;
     P.cuts_off = P.samples_off + ((size_t)P.sample_cap * 8 + 255) / 256 * 256;
-    P.bytes = P.cuts_off + (size_t)kMaxLists * P.sample_cap * 4;
+    P.header_off = (P.cuts_off + (size_t)kMaxLists * P.sample_cap * 4 + 255) / 256 * 256;
+    P.bytes = P.header_off + sizeof(PublishHeader);
     return P;
 }
 
@@ -1094,8 +1097,15 @@ int ensure_publish(astre_gpu_ctx *ctx, uint32_t parity)
 {
     if (ctx->d_publish[parity]) return ASTRE_OK;
     void *p = nullptr;
-    CK(cudaMalloc(&p, publish_layout(ctx->max_keys).bytes));
+    const PublishLayout P = publish_layout(ctx->max_keys);
+    CK(cudaMalloc(&p, P.bytes));
+    CK(cudaMemset(static_cast<unsigned char *>(p) + P.header_off, 0, sizeof(PublishHeader)));      // flags start at epoch 0
     ctx->d_publish[parity] = static_cast<unsigned char *>(p);
+    if (!ctx->d_merge_error) {      // allocated here, not inside the per-frame calls: those must never block on the device
+        CK(cudaMalloc(&ctx->d_merge_error, sizeof(uint32_t)));
+        CK(cudaMemset(ctx->d_merge_error, 0, sizeof(uint32_t)));
+    }
+    if (!ctx->d_mdims) CK(cudaMalloc(&ctx->d_mdims, sizeof(MergeDims)));
     return ASTRE_OK;
 }
 
@@ -1122,6 +1132,31 @@ int fill_lists(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_lists, const uint64
     return ASTRE_OK;
 }
 
+// Output and tile-table buffers of a merge.  May free and reallocate (which waits for the device): the flows that
+// enqueue kernels waiting on other GPUs call this BEFORE they enqueue anything.
+int ensure_merge_buffers(astre_gpu_ctx *ctx, uint64_t out_count, uint32_t n_samples, bool exact)
+{
+    if (ctx->cap_merged < out_count || !ctx->d_merged_keys) {
+        if (ctx->d_merged_keys) CK(cudaFree(ctx->d_merged_keys));
+        if (ctx->d_merged_src) CK(cudaFree(ctx->d_merged_src));
+        ctx->d_merged_keys = nullptr; ctx->d_merged_src = nullptr; ctx->cap_merged = 0;
+        const uint64_t cap = std::max<uint64_t>(exact ? out_count : out_count + out_count / 4, 1024);
+        CK(cudaMalloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_merged_src, cap));
+        ctx->cap_merged = cap;
+    }
+    if (ctx->cap_merge_tiles < n_samples + 1 || !ctx->d_splits) {
+        if (ctx->d_splits) CK(cudaFree(ctx->d_splits));
+        if (ctx->d_tile_start) CK(cudaFree(ctx->d_tile_start));
+        ctx->d_splits = nullptr; ctx->d_tile_start = nullptr; ctx->cap_merge_tiles = 0;
+        const uint32_t cap = exact ? n_samples + 1 : n_samples + n_samples / 4 + 64;
+        CK(cudaMalloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
+        ctx->cap_merge_tiles = cap;
+    }
+    return ASTRE_OK;
+}
+
 // table + tiles, given lists, samples and cut tables.  Host-side sizes (L.dev_dims == nullptr): out_first /
 // out_count select the window.  Device-side sizes: n_samples_cap bounds the sample count, the window is slice
 // slice_rank of slice_world (0 = whole list) and at most out_count keys.
@@ -1134,24 +1169,7 @@ int merge_tail(astre_gpu_ctx *ctx, const MergeLists &L, uint64_t out_first, uint
         out_first = std::min<uint64_t>(out_first, L.d.total);
         out_count = std::min<uint64_t>(out_count, L.d.total - out_first);
     }
-    if (ctx->cap_merged < out_count || !ctx->d_merged_keys) {
-        if (ctx->d_merged_keys) CK(cudaFree(ctx->d_merged_keys));
-        if (ctx->d_merged_src) CK(cudaFree(ctx->d_merged_src));
-        ctx->d_merged_keys = nullptr; ctx->d_merged_src = nullptr; ctx->cap_merged = 0;
-        const uint64_t cap = std::max<uint64_t>(dev ? out_count : out_count + out_count / 4, 1024);
-        CK(cudaMalloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_merged_src, cap));
-        ctx->cap_merged = cap;
-    }
-    if (ctx->cap_merge_tiles < n_samples + 1 || !ctx->d_splits) {
-        if (ctx->d_splits) CK(cudaFree(ctx->d_splits));
-        if (ctx->d_tile_start) CK(cudaFree(ctx->d_tile_start));
-        ctx->d_splits = nullptr; ctx->d_tile_start = nullptr; ctx->cap_merge_tiles = 0;
-        const uint32_t cap = dev ? n_samples + 1 : n_samples + n_samples / 4 + 64;
-        CK(cudaMalloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
-        ctx->cap_merge_tiles = cap;
-    }
+    if (int rc = ensure_merge_buffers(ctx, out_count, n_samples, dev)) return rc;
     if (n_samples && out_count) {
         cudaLaunchAttribute pdl;
         pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1205,7 +1223,8 @@ int astre_gpu_publish_keys(astre_gpu_ctx *ctx, uint32_t parity, void *stream)
     k_publish_keys<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc->skip, ctx->last_sort_passes,
                                                      &ctx->d_ctl->key_total, ctx->max_keys,
                                                      reinterpret_cast<unsigned long long *>(base),
-                                                     reinterpret_cast<unsigned long long *>(base + publish_layout(ctx->max_keys).samples_off));
+                                                     reinterpret_cast<unsigned long long *>(base + publish_layout(ctx->max_keys).samples_off),
+                                                     nullptr, 0u, nullptr);
     CK_LAUNCH();
     return ASTRE_OK;
 }
@@ -1397,6 +1416,76 @@ int astre_gpu_merge_published_dev(astre_gpu_ctx *ctx, uint32_t n_lists, const vo
     return merge_tail(ctx, L, 0, out_cap, slice_rank, slice_world, n_samples_cap, s);
 }
 
+// The whole exchange over NVLink peer memory, no NCCL and no host round trip: counts and "ready" flags travel in
+// the publish buffers' headers, tiny one-warp kernels signal and poll them.  One call per frame and rank:
+//   wait(peers are done reading my buffer of epoch-2) -> publish keys, samples, counts
+//   -> signal "published", wait for the peers', list sizes from their counts -> cut table of my own list
+//   -> signal "cuts", wait for the peers' -> tile table -> merge (keys pulled from the peers) -> signal "read".
+// `epoch` is the frame number: the same on every rank, starting at 1, +1 per call; the buffer used is epoch & 1.
+int astre_gpu_merge_p2p(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish0,
+                        const void *const *publish1, uint32_t epoch, uint32_t slice_rank, uint32_t slice_world,
+                        uint64_t out_cap, void *stream)
+{
+    if (!ctx || !publish0 || !publish1 || rank >= n_lists || epoch == 0 || (slice_world && slice_rank >= slice_world))
+        return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    if (!(ctx->last_flags & ASTRE_FRAME_SORT)) return fail(ctx, ASTRE_ERR_STATE, "the global list needs a sorted frame (ASTRE_FRAME_SORT)");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t parity = epoch & 1u;
+    const void *const *publish = parity ? publish1 : publish0;
+    MergeLists L;
+    if (int rc = lists_from_publish(ctx, L, n_lists, publish)) return rc;
+    if (publish[rank] != ctx->d_publish[parity] || !ctx->d_publish[parity])
+        return fail(ctx, ASTRE_ERR_INVALID, "publish%u[rank] must be this context's own publish buffer", parity);
+    const PublishLayout P = publish_layout(ctx->max_keys);
+    PeerHeaders H{};
+    H.n = n_lists; H.self = rank;
+    for (uint32_t t = 0; t < n_lists; ++t)
+        H.h[t] = reinterpret_cast<PublishHeader *>(const_cast<unsigned char *>(static_cast<const unsigned char *>(publish[t])) + P.header_off);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n_views = ctx->views_per_world;
+    if (n_views == 0 || n_views > ASTRE_MAX_VIEWS) return fail(ctx, ASTRE_ERR_STATE, "no views set");
+    const uint64_t whole = (uint64_t)n_lists * ctx->max_keys;
+    if (out_cap == 0) out_cap = slice_world ? (whole + slice_world - 1) / slice_world : whole;
+    const uint32_t n_samples_cap = n_lists * P.sample_cap;
+    if (int rc = ensure_merge_buffers(ctx, out_cap, n_samples_cap, true)) return rc;      // nothing below may block on the device
+    if (int rc = merge_begin(ctx, s)) return rc;
+
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+    MergeDims *no_dims = nullptr;
+    const unsigned long long cap = ctx->max_keys;
+    // my buffer of this parity was last read by the peers for epoch-2
+    if (epoch > 2) {
+        k_peer_sync<<<1, 32, 0, s>>>(H, kNoFlag, 0u, 2u, epoch - 2u, no_dims, no_dims, 0u, cap, ctx->d_merge_error);
+        CK_LAUNCH();
+    }
+    unsigned char *base = ctx->d_publish[parity];
+    cfg.gridDim = dim3((unsigned)ctx->sm_count * 4u); cfg.blockDim = dim3(256);
+    CK(cudaLaunchKernelEx(&cfg, k_publish_keys, (const unsigned long long *)ctx->d_keys[0], (const unsigned long long *)ctx->d_keys[1],
+                          (const uint32_t *)ctx->d_sc->skip, ctx->last_sort_passes, (const unsigned long long *)&ctx->d_ctl->key_total, cap,
+                          reinterpret_cast<unsigned long long *>(base), reinterpret_cast<unsigned long long *>(base + P.samples_off),
+                          (const uint32_t *)ctx->d_counts, n_views, H.h[rank]));
+    CK_LAUNCH();
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32);
+    CK(cudaLaunchKernelEx(&cfg, k_peer_sync, H, 0u, epoch, 0u, epoch, ctx->d_mdims, ctx->d_mdims, n_views, cap, ctx->d_merge_error));
+    CK_LAUNCH();
+    uint32_t *own_cuts = const_cast<uint32_t *>(L.cuts[rank]);
+    k_merge_cuts<<<(uint32_t)ctx->sm_count * 8u, 256, 0, s>>>(L, rank, own_cuts, 0);
+    CK_LAUNCH();
+    CK(cudaLaunchKernelEx(&cfg, k_peer_sync, H, 1u, epoch, 1u, epoch, no_dims, ctx->d_mdims, 0u, cap, ctx->d_merge_error));
+    CK_LAUNCH();
+    if (int rc = merge_tail(ctx, L, 0, out_cap, slice_rank, slice_world, n_samples_cap, s)) return rc;
+    k_peer_sync<<<1, 32, 0, s>>>(H, 2u, epoch, kNoFlag, 0u, no_dims, no_dims, 0u, cap, ctx->d_merge_error);
+    CK_LAUNCH();
+    CK(cudaEventRecord(ctx->ev_merge1, s));
+    ctx->merge_p2p_flags = true;
+    return ASTRE_OK;
+}
+
 void *astre_gpu_device_merged_keys(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_keys : nullptr; }
 void *astre_gpu_device_merged_sources(astre_gpu_ctx *ctx) { return ctx ? ctx->d_merged_src : nullptr; }
 
@@ -1406,6 +1495,14 @@ static int merged_count(astre_gpu_ctx *ctx, uint64_t *n_out)
     if (!ctx->merge_done) return fail(ctx, ASTRE_ERR_STATE, "no merge has been run");
     if (ctx->merge_dev) {
         CK(cudaStreamSynchronize(ctx->merge_stream));
+        if (ctx->d_merge_error) {
+            uint32_t err = 0;
+            CK(cudaMemcpy(&err, ctx->d_merge_error, sizeof err, cudaMemcpyDeviceToHost));
+            if (err) {
+                CK(cudaMemset(ctx->d_merge_error, 0, sizeof err));
+                return fail(ctx, ASTRE_ERR_STATE, "peer %u did not signal within the time limit: the merged list is invalid", err - 1u);
+            }
+        }
         MergeDims d;
         CK(cudaMemcpy(&d, ctx->d_mdims, sizeof d, cudaMemcpyDeviceToHost));
         uint64_t first = 0, count = d.total;

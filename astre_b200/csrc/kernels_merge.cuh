@@ -281,14 +281,80 @@ k_merge_tiles(const __grid_constant__ MergeLists L, const uint32_t *__restrict__
     }
 }
 
+// ---- exchange without NCCL: flags and counts in the publish buffers, polled over NVLink ------------------
+//
+// The last 256 bytes of a publish buffer.  Peers read `counts` and poll the flags through their CUDA IPC
+// mapping; every flag holds the epoch (frame number, from 1) up to which the statement is true.
+struct PublishHeader {
+    uint32_t counts[ASTRE_MAX_VIEWS];   // per-view visible counts of the published frame
+    uint32_t flag[3];                   // [0] keys + samples + counts complete, [1] cut table complete,
+                                        // [2] this rank has finished reading its peers' buffers
+    uint32_t pad[29];
+};
+static_assert(sizeof(PublishHeader) == 256, "PublishHeader layout");
+
+struct PeerHeaders { PublishHeader *h[kMaxLists]; uint32_t n, self; };
+
+constexpr uint32_t kNoFlag = 0xFFu;
+constexpr long long kPeerTimeoutCycles = 4000000000ll;       // ~2 s: a peer that never signals must not hang the GPU
+
+// One warp.  (1) signal: own flag[sig] = sig_epoch, after everything this stream ran before.  (2) wait: lane r
+// polls peer r's flag[wait] until it reaches wait_epoch.  (3) optionally the list sizes from the peers' counts.
+// After a time-out the sizes in `void_dims` are zeroed, which turns the kernels that follow into no-ops.
+__global__ void k_peer_sync(const PeerHeaders H, const uint32_t sig, const uint32_t sig_epoch, const uint32_t wait,
+                            const uint32_t wait_epoch, MergeDims *__restrict__ dims, MergeDims *__restrict__ void_dims,
+                            const uint32_t n_views, const unsigned long long max_keys, uint32_t *__restrict__ error)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t lane = threadIdx.x;
+    if (sig != kNoFlag && lane == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&H.h[H.self]->flag[sig]), "r"(sig_epoch) : "memory");
+    }
+    if (wait != kNoFlag && lane < H.n && lane != H.self) {
+        const long long t0 = clock64();
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&H.h[lane]->flag[wait]) : "memory");
+            if (v >= wait_epoch) break;
+            if (clock64() - t0 > kPeerTimeoutCycles) { *error = 1u + lane; break; }
+            __nanosleep(200);
+        }
+    }
+    __syncwarp();
+    if (*(volatile uint32_t *)error) {               // a peer never signalled: make the rest of the chain a no-op
+        if (lane == 0 && void_dims) { void_dims->total = 0; void_dims->sample_base[H.n] = 0; }
+        return;
+    }
+    if (dims && lane == 0) {
+        unsigned long long total = 0;
+        uint32_t n_samples = 0;
+        for (uint32_t t = 0; t < H.n; ++t) {
+            unsigned long long c = 0;
+            for (uint32_t v = 0; v < n_views; ++v) c += H.h[t]->counts[v];
+            if (c > max_keys) c = max_keys;
+            dims->n[t] = (uint32_t)c;
+            dims->sample_base[t] = n_samples;
+            n_samples += (uint32_t)((c + kSampleStep - 1) >> kSampleShift);
+            total += c;
+        }
+        dims->sample_base[H.n] = n_samples;
+        dims->n_lists = H.n;
+        dims->total = total;
+    }
+}
+
 // Copies the frame's sorted list (whichever sort buffer it ended in) into a buffer at a fixed
 // address, with its samples behind it: what a peer GPU maps.  Everything is read on the device;
 // no host round trip.
 __global__ void __launch_bounds__(256)
 k_publish_keys(const unsigned long long *__restrict__ buf0, const unsigned long long *__restrict__ buf1,
                const uint32_t *__restrict__ skip, uint32_t n_passes, const unsigned long long *__restrict__ key_total,
-               unsigned long long cap, unsigned long long *__restrict__ dst, unsigned long long *__restrict__ samples)
+               unsigned long long cap, unsigned long long *__restrict__ dst, unsigned long long *__restrict__ samples,
+               const uint32_t *__restrict__ counts, uint32_t n_views, PublishHeader *__restrict__ header)
 {
+    cudaGridDependencySynchronize();
+    if (header && blockIdx.x == 0 && threadIdx.x < n_views) header->counts[threadIdx.x] = counts[threadIdx.x];
     uint32_t which = 0;
     for (uint32_t p = 0; p < n_passes; ++p) which ^= skip[p] ? 0u : 1u;
     const unsigned long long *src = which ? buf1 : buf0;

@@ -272,6 +272,15 @@ class GpuContext:
         ptrs = (C.c_void_p * g)(*[int(p) if p else None for p in publish_ptrs])
         self._check(self._lib.astre_gpu_merge_published_dev(self._h, g, ptrs, int(slice_rank), int(slice_world), int(out_cap), stream))
 
+    def merge_p2p(self, rank, publish0, publish1, epoch, slice_rank=0, slice_world=0, out_cap=0, stream=None):
+        """The whole exchange over NVLink peer memory (no NCCL, no host round trip): publish, wait for the peers,
+        cut table, wait, merge.  publish0 / publish1: all ranks' publish buffers of parity 0 / 1; epoch: frame number from 1."""
+        g = len(publish0)
+        p0 = (C.c_void_p * g)(*[int(p) if p else None for p in publish0])
+        p1 = (C.c_void_p * g)(*[int(p) if p else None for p in publish1])
+        self._check(self._lib.astre_gpu_merge_p2p(self._h, g, int(rank), p0, p1, int(epoch), int(slice_rank), int(slice_world),
+                                                  int(out_cap), stream))
+
     def merged_count(self):
         n = C.c_uint64()
         self._check(self._lib.astre_gpu_merged_count(self._h, C.byref(n)))

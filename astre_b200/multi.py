@@ -107,6 +107,7 @@ class GlobalDrawList:
         self.peer[self.rank] = list(self.local)
         self._gathered = None
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._epoch = 0
         if mode == "p2p" and self.world > 1:
             mine = [self.max_keys, ctx.export_handle(0), ctx.export_handle(1)]
             handles = [None] * self.world
@@ -131,6 +132,16 @@ class GlobalDrawList:
         if self.world > 1:
             dist.all_reduce(self._token, group=self.group)                       # device-side barrier
         self.ctx.merge_published_dev(ptrs, self.rank if sliced else 0, self.world if sliced else 0, out_cap, stream)
+
+    def build_flags(self, sliced=False, out_cap=0, stream=None):
+        """Peer-to-peer flow without NCCL: counts and ready flags travel in the publish buffers and are polled
+        over NVLink by the library's own kernels.  Call once per frame on every rank (after ctx.frame());
+        the epoch counter lives here and must advance in step on all ranks."""
+        assert self.mode == "p2p" or self.world == 1
+        self._epoch += 1
+        p0 = [self.peer[r][0] for r in range(self.world)]
+        p1 = [self.peer[r][1] for r in range(self.world)]
+        self.ctx.merge_p2p(self.rank, p0, p1, self._epoch, self.rank if sliced else 0, self.world if sliced else 0, out_cap, stream)
 
     def build(self, frame_index, sliced=False, stream=None):
         """Call after ctx.frame().  Returns (all_counts [G, F] on the host, out_first, out_count): the

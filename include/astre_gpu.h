@@ -291,6 +291,16 @@ ASTRE_API int astre_gpu_merge_prepare_dev(astre_gpu_ctx *ctx, uint32_t n_lists, 
                                           const uint32_t *all_counts_dev, uint32_t n_views, void *stream);
 ASTRE_API int astre_gpu_merge_published_dev(astre_gpu_ctx *ctx, uint32_t n_lists, const void *const *publish,
                                             uint32_t slice_rank, uint32_t slice_world, uint64_t out_cap, void *stream);
+/* (b) without NCCL and without a host round trip: counts and "ready" flags
+ * travel in the publish buffers' headers and are polled over NVLink by one-warp
+ * kernels.  One call per frame and rank does publish -> wait for the peers ->
+ * cut table -> wait -> merge.  publish0 / publish1: the publish buffers of all
+ * ranks for parity 0 / 1 (own and imported); epoch: the frame number, the same
+ * on every rank, from 1, +1 per call.  A peer that never signals makes
+ * astre_gpu_merged_count / _read_merged fail after ~2 s instead of hanging. */
+ASTRE_API int astre_gpu_merge_p2p(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, const void *const *publish0,
+                                  const void *const *publish1, uint32_t epoch, uint32_t slice_rank, uint32_t slice_world,
+                                  uint64_t out_cap, void *stream);
 /* Keys kept by the last merge (synchronises if the sizes were computed on the device). */
 ASTRE_API int astre_gpu_merged_count(astre_gpu_ctx *ctx, uint64_t *n_out);
 /* Result of the last merge: keys[i], sources[i] (= rank) for global position

@@ -45,6 +45,17 @@ def main():
                 assert np.array_equal(src, o_src[first:first + count]), (mode, sliced, "sources differ")
                 if sliced:
                     assert count < len(o_keys)
+            if mode == "p2p":                     # no NCCL at all: flags and counts polled over NVLink
+                for sliced in (False, True, True, False):
+                    ctx.frame()
+                    g.build_flags(sliced=sliced)
+                    per = -(-len(o_keys) // world)
+                    first = min(rank * per, len(o_keys)) if sliced else 0
+                    count = min(per, len(o_keys) - first) if sliced else len(o_keys)
+                    assert ctx.merged_count() == count, (ctx.merged_count(), count)
+                    keys, src = ctx.read_merged(0, count)
+                    assert np.array_equal(keys, o_keys[first:first + count]), ("flags", sliced, "keys differ")
+                    assert np.array_equal(src, o_src[first:first + count]), ("flags", sliced, "sources differ")
             if mode == "p2p":                     # same flow, key counts never leave the device
                 for sliced in (True, False):
                     ctx.frame()

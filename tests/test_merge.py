@@ -120,6 +120,21 @@ def test_gpu_merge_of_range_shards(oracle, n, g):
         assert last.merged_count() == total
         k5, s5 = last.read_merged(0, total)
         assert np.array_equal(k5, o_keys) and np.array_equal(s5, o_src)
+        # no NCCL, no host: flags and counts in the publish buffers, polled by one-warp kernels.  Every "rank"
+        # enqueues its whole chain; the chains wait for one another on the device (each context has its own stream)
+        p0 = [c.device_published_keys_ptr(0) for c in ctxs]
+        p1 = [c.device_published_keys_ptr(1) for c in ctxs]
+        for r in range(g):      # size every context's buffers first: in ONE process a reallocation (cudaFree waits for the
+            ctxs[r].merge_prepare_dev(r, ptrs, table.data_ptr(), scene.views_per_world)     # device) would stall the other
+            ctxs[r].merge_published_dev(ptrs)                                               # "ranks" chains mid-wait
+            ctxs[r].sync()
+        for epoch in (1, 2, 3):
+            for r in range(g):
+                ctxs[r].merge_p2p(r, p0, p1, epoch)
+            for r in (0, g - 1):
+                assert ctxs[r].merged_count() == total
+                k7, s7 = ctxs[r].read_merged(0, total)
+                assert np.array_equal(k7, o_keys) and np.array_equal(s7, o_src), f"flags flow, epoch {epoch}, rank {r}"
         per = -(-total // g)
         for r in (0, g - 1):
             ctxs[r].merge_prepare_dev(r, ptrs, table.data_ptr(), scene.views_per_world)

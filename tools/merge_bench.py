@@ -125,6 +125,20 @@ def distributed(args):
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             out[name + "_ordered"] = bool(ok.item())
 
+        g2 = multi.GlobalDrawList(ctx, 5, max_keys, mode="p2p")      # no NCCL: flags + counts in the publish buffers
+        for sliced in (False, True):
+            def step():
+                ctx.frame()
+                g2.build_flags(sliced=sliced)
+            name = f"p2p_flags{'_sliced' if sliced else ''}"
+            out[name + "_ms"] = timed(step)
+            out[name + "_merge_kernels_ms"] = ctx.last_merge_ms()
+            count = ctx.merged_count()
+            keys, src = merged_tensors(ctx, count, dev)
+            ok = torch.tensor([1 if check_order(keys, src) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            out[name + "_ordered"] = bool(ok.item())
+
         def frame_no_sync():
             ctx.frame()
             multi.exchange_counts(counts_dev)
