@@ -220,10 +220,23 @@ k_merge_tiles(const __grid_constant__ MergeLists L, const uint32_t *__restrict__
         }
         __syncthreads();
         const uint32_t total = s_run[0][G];
-        for (uint32_t t = 0; t < G; ++t) {
-            const uint32_t off_t = s_run[0][t], len_t = s_run[0][t + 1] - off_t;
-            const unsigned long long *src = L.keys[t] + s_lo[t];
-            for (uint32_t i = tid; i < len_t; i += kMergeThreads) { s_keys[0][off_t + i] = src[i]; s_tag[0][off_t + i] = (uint8_t)t; }
+        // stage the runs: four independent loads in flight per thread (over NVLink one load costs microseconds)
+        for (uint32_t e0 = tid; e0 < total; e0 += kMergeThreads * 4u) {
+            unsigned long long v[4];
+            uint32_t tt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + (uint32_t)u * kMergeThreads;
+                uint32_t t = 0;
+                while (t + 1 < G && e >= s_run[0][t + 1]) ++t;
+                tt[u] = t;
+                v[u] = e < total ? L.keys[t][s_lo[t] + (e - s_run[0][t])] : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t e = e0 + (uint32_t)u * kMergeThreads;
+                if (e < total) { s_keys[0][e] = v[u]; s_tag[0][e] = (uint8_t)tt[u]; }
+            }
         }
         __syncthreads();
         uint32_t cur = 0;
