@@ -69,6 +69,7 @@ struct astre_gpu_ctx {
                                           // (measured r1: 0.434 vs 0.441 ms on config 3, but 0.78 vs 0.55 ms on a dense scene)
     uint32_t *d_block_hist = nullptr;     // [hist_regions][8][256] partial digit histograms
     uint32_t hist_regions = 0;
+    uint32_t claim_groups = 8;            // work counters of the fused kernel in a flat frame (ASTRE_CLAIM_GROUPS; 0 = per-CTA shared counters)
     uint32_t shader_or = 0;               // OR of every shader id uploaded (live bits of the key's shader field)
     int sort_threads = 256;               // CTA size of k_sort_pass (ASTRE_SORT_THREADS = 256 | 1024), 8 keys per thread
     int sort_grid = 148;                  // co-resident CTAs of k_sort_pass
@@ -179,6 +180,7 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     P.ctl = c->d_ctl;
     P.block_hist = c->d_block_hist;
     P.hist_regions = c->hist_regions;
+    P.claim_groups = c->claim_groups;
     P.key_cap = c->max_keys;
     P.n_meshes = c->n_meshes;
     P.views_per_world = cull ? c->views_per_world : 0u;
@@ -198,6 +200,7 @@ __global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *coun
         sc->n_keys = 0; sc->epoch = epoch;
     }
     if (tid < kSortPasses) sc->skip[tid] = 1;
+    for (uint32_t i = tid; i < (uint32_t)(kClaimGroups * kClaimStride); i += nth) ctl->claim[i] = 0;
     for (uint32_t i = tid; i < n_counts; i += nth) counts[i] = 0;
     for (uint32_t i = tid; i < n_hist_words; i += nth) block_hist[i] = 0;
 }
@@ -406,6 +409,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     ctx->cap_long_runs = (uint32_t)std::min<uint64_t>(ctx->max_keys / kShortRun + 1, 1u << 22);
     CKC(cudaMalloc(&ctx->d_long_runs, (size_t)ctx->cap_long_runs * sizeof(uint32_t)));
     if (std::getenv("ASTRE_SORT_TIES")) ctx->sort_ties = true;
+    if (const char *m = std::getenv("ASTRE_CLAIM_GROUPS")) ctx->claim_groups = (uint32_t)std::max(std::atoi(m), 0);
     // partial sort histograms: CTAs of the fused kernel add (RED) into region blockIdx % 8.  Measured on config 3:
     // 296 regions (one per CTA) 0.4447 ms per frame, 32: 0.4371, 8: 0.4357, 1: 0.4369 -- fewer words to clear and to sum.
     ctx->hist_regions = 8u;

@@ -301,12 +301,24 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     const uint32_t base0 = first & ~(uint32_t)(kWarpTile - 1);
     const uint32_t n_tiles = (end - base0 + kBlockTile - 1) / kBlockTile;
 
-    // The CTA owns block tiles blockIdx.x, blockIdx.x + gridDim.x, ...; its warps take the warp tiles of that list
-    // (index j: block tile j / 8, warp tile j % 8) from a shared counter instead of a fixed warp -> sub-tile
-    // mapping, so a warp that falls behind does not keep the CTA (and its half of the SM) waiting at the end.
-    const uint32_t n_wtiles = blockIdx.x < n_tiles ? ((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * kWarpsPerBlock : 0u;
+    // Work distribution.  Warp tiles are not bound to warps:
+    //  * one flat range (the common case): CTA b belongs to group b % n_groups; group g owns block tiles g,
+    //    g + n_groups, ... and all warps of the group take the warp tiles of that list from one global counter, two
+    //    claims ahead so that the atomic's latency never shows.  Measured on config 3 (ms for transform + cull):
+    //    fixed mapping 0.334, per-CTA shared counter 0.319, groups of 2 CTAs 0.315, 4: 0.308, 8: 0.307,
+    //    37: 0.304, 74: 0.303, one counter for the grid 0.307 -> 8 groups;
+    //  * hierarchy levels: the CTA owns block tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its 8
+    //    warps take the warp tiles of that list from a shared-memory counter;
+    //  * batched worlds: fixed warp -> warp tile mapping (claiming measured 2 % slower there).
+    // A warp that falls behind therefore does not keep its CTA -- and its SM -- waiting at the end of the launch.
+    // (flat frames only: they have exactly one launch per frame, and the counters are zeroed once per frame)
+    const bool gclaim = !HIER && !WORLDS && LT.n == 1 && P.claim_groups != 0;
+    const uint32_t n_groups = gclaim ? min(min(P.claim_groups, (uint32_t)kClaimGroups), gridDim.x) : gridDim.x;
+    const uint32_t group = blockIdx.x % n_groups;
+    const uint32_t n_wtiles = group < n_tiles ? ((n_tiles - group + n_groups - 1) / n_groups) * kWarpsPerBlock : 0u;
+    uint32_t *gcounter = &P.ctl->claim[group * kClaimStride];
     auto wtile_base = [&](uint32_t j) {
-        return base0 + (blockIdx.x + (j / kWarpsPerBlock) * gridDim.x) * kBlockTile + (j % kWarpsPerBlock) * kWarpTile;
+        return base0 + (group + (j / kWarpsPerBlock) * n_groups) * kBlockTile + (j % kWarpsPerBlock) * kWarpTile;
     };
     // lane 0: one bulk copy of the warp tile's record (+ its world's view records into cache half `half`)
     auto issue = [&](uint32_t j, uint32_t half) {
@@ -322,9 +334,20 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
             bulk_g2s(s_in_addr, P.tiles + (size_t)(wb0 >> 7) * kTileFloats, kInBytes, bar);
         }
     };
-    if ((uint32_t)warp < n_wtiles && lane == 0) issue((uint32_t)warp, parity);
+    uint32_t j = (uint32_t)warp, jn = 0, jnn_lane0 = 0;
+    if (gclaim) {
+        uint32_t a = 0, b = 0;
+        if (lane == 0) { a = atomicAdd(gcounter, 1u); b = atomicAdd(gcounter, 1u); }
+        j = __shfl_sync(0xffffffffu, a, 0);
+        jn = __shfl_sync(0xffffffffu, b, 0);
+    }
+    if (j < n_wtiles && lane == 0) issue(j, parity);
+    auto advance = [&]() {
+        j = jn;
+        if (gclaim) jn = __shfl_sync(0xffffffffu, jnn_lane0, 0);      // claimed a whole tile ago
+    };
 
-    for (uint32_t j = (uint32_t)warp, jn = 0; j < n_wtiles; j = jn) {
+    for (; j < n_wtiles; advance()) {
         const uint32_t wbase = wtile_base(j);
         const bool full = wbase >= first && wbase + kWarpTile <= end;   // warp-uniform
 
@@ -343,13 +366,19 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
         }
         __syncwarp();   // every lane holds its inputs: the buffer may be refilled
         {
-            // batched worlds keep the fixed mapping (measured: config 5 is 2 % slower with claiming, config 3 2.5 % faster)
-            uint32_t claimed = j + kWarpsPerBlock;
-            if (lane == 0) {
-                if (!WORLDS) claimed = atomicAdd(&s_claim, 1u);
-                if (claimed < n_wtiles) issue(claimed, parity);
+            if (gclaim) {
+                if (lane == 0) {
+                    if (jn < n_wtiles) issue(jn, parity);
+                    jnn_lane0 = atomicAdd(gcounter, 1u);           // needed one tile from now
+                }
+            } else {
+                uint32_t claimed = j + kWarpsPerBlock;              // batched worlds: fixed mapping
+                if (lane == 0) {
+                    if (!WORLDS) claimed = atomicAdd(&s_claim, 1u);
+                    if (claimed < n_wtiles) issue(claimed, parity);
+                }
+                jn = WORLDS ? claimed : __shfl_sync(0xffffffffu, claimed, 0);
             }
-            jn = WORLDS ? claimed : __shfl_sync(0xffffffffu, claimed, 0);
         }
 
         WorldBounds wb[kPerLane];

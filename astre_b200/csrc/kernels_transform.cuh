@@ -63,10 +63,12 @@ struct BoundsDev {   // 32 B; extents and radius are >= 0 (checked by astre_gpu_
     uint32_t reserved;
 };
 
+constexpr int kClaimGroups = 64, kClaimStride = 32;
 struct FrameControl {            // one per context, reset at the start of a frame
     unsigned long long key_total; // keys reserved so far (may exceed capacity)
     uint32_t overflow;
     uint32_t barrier;             // arrivals at the grid barrier of multi-level launches
+    uint32_t claim[kClaimGroups * kClaimStride];   // next unclaimed warp tile of every CTA group (one 128-byte line each)
 };
 
 struct FrameParams {
@@ -79,6 +81,7 @@ struct FrameParams {
     FrameControl *ctl;
     uint32_t *block_hist;          // [hist_regions][8][256] partial digit histograms for the sort
     uint32_t hist_regions;         // CTA b adds into region b % hist_regions
+    uint32_t claim_groups;         // work counters of a flat frame (0: none); CTA b draws from group b % claim_groups
     unsigned long long key_cap;
     uint32_t n_meshes;
     uint32_t views_per_world;      // 0 = no culling
