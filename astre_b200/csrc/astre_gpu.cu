@@ -742,7 +742,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         const uint32_t fused_grid = (uint32_t)(ctx->sm_count * ctx->fused_blocks_per_sm);
         // one launch over a list of slot ranges; hier = world[parent] * local (ranges after the first wait for
         // the previous one through a grid barrier, hence the cooperative launch)
-        uint32_t barrier_rounds = 0;
+        uint32_t barrier_rounds = 0, claim_sets = 0;
         cudaError_t launch_err = cudaSuccess;
         auto launch_ranges = [&](const LevelTable &LT, bool hier) {
             uint32_t tiles = 0;
@@ -759,6 +759,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             if (LT.n > 1) launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
             else launch_err = cudaLaunchKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
             barrier_rounds += (LT.n - 1) * g;
+            claim_sets += LT.n * std::min<uint32_t>(ctx->claim_groups, g);
         };
         if (!ctx->has_parents) {
             LevelTable LT{};
@@ -783,6 +784,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
                 }
                 LevelTable LT{};
                 LT.barrier_base = barrier_rounds;
+                LT.claim_base = claim_sets;                   // the kernel falls back to per-CTA counters when the sets run out
                 while (l < ctx->levels.size() && ctx->levels[l].contiguous && ctx->levels[l].count >= ctx->small_level &&
                        LT.n < (uint32_t)kMaxLevelsPerLaunch && (ctx->coop_launch || LT.n == 0)) {
                     LT.first[LT.n] = ctx->levels[l].first;

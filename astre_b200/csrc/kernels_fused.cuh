@@ -84,6 +84,7 @@ constexpr int kMaxLevelsPerLaunch = 32;
 struct LevelTable {
     uint32_t n;
     uint32_t barrier_base;                       // barrier arrivals already counted in this frame
+    uint32_t claim_base;                         // first work counter of this launch (level l uses the next n_groups)
     uint32_t first[kMaxLevelsPerLaunch], end[kMaxLevelsPerLaunch];
 };
 
@@ -307,16 +308,19 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     //    claims ahead so that the atomic's latency never shows.  Measured on config 3 (ms for transform + cull):
     //    fixed mapping 0.334, per-CTA shared counter 0.319, groups of 2 CTAs 0.315, 4: 0.308, 8: 0.307,
     //    37: 0.304, 74: 0.303, one counter for the grid 0.307 -> 8 groups;
-    //  * hierarchy levels: the CTA owns block tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its 8
-    //    warps take the warp tiles of that list from a shared-memory counter;
-    //  * batched worlds: fixed warp -> warp tile mapping (claiming measured 2 % slower there).
+    //    batched worlds the same (config 5: 1.439 -> 1.391 ms);
+    //  * hierarchy levels: the CTA owns block tiles blockIdx.x, blockIdx.x + gridDim.x, ... and its 8 warps take the
+    //    warp tiles of that list from a shared-memory counter (global counters cost two exposed atomics at the start
+    //    of every level: config 2 0.140 -> 0.178 ms).
     // A warp that falls behind therefore does not keep its CTA -- and its SM -- waiting at the end of the launch.
-    // (flat frames only: they have exactly one launch per frame, and the counters are zeroed once per frame)
-    const bool gclaim = !HIER && !WORLDS && LT.n == 1 && P.claim_groups != 0;
-    const uint32_t n_groups = gclaim ? min(min(P.claim_groups, (uint32_t)kClaimGroups), gridDim.x) : gridDim.x;
+    // (the counters are zeroed once per frame: every level of every launch of a frame gets its own set)
+    const uint32_t want_groups = min(min(P.claim_groups, (uint32_t)kClaimGroups), gridDim.x);
+    const bool gclaim = want_groups != 0 && !HIER &&
+                        LT.claim_base + (level + 1) * want_groups <= (uint32_t)kClaimGroups;
+    const uint32_t n_groups = gclaim ? want_groups : gridDim.x;
     const uint32_t group = blockIdx.x % n_groups;
     const uint32_t n_wtiles = group < n_tiles ? ((n_tiles - group + n_groups - 1) / n_groups) * kWarpsPerBlock : 0u;
-    uint32_t *gcounter = &P.ctl->claim[group * kClaimStride];
+    uint32_t *gcounter = &P.ctl->claim[(gclaim ? LT.claim_base + level * n_groups + group : 0u) * kClaimStride];
     auto wtile_base = [&](uint32_t j) {
         return base0 + (group + (j / kWarpsPerBlock) * n_groups) * kBlockTile + (j % kWarpsPerBlock) * kWarpTile;
     };
@@ -372,7 +376,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
                     jnn_lane0 = atomicAdd(gcounter, 1u);           // needed one tile from now
                 }
             } else {
-                uint32_t claimed = j + kWarpsPerBlock;              // batched worlds: fixed mapping
+                uint32_t claimed = j + kWarpsPerBlock;              // batched worlds without counters: fixed mapping
                 if (lane == 0) {
                     if (!WORLDS) claimed = atomicAdd(&s_claim, 1u);
                     if (claimed < n_wtiles) issue(claimed, parity);
