@@ -3,8 +3,11 @@
 //
 // Work decomposition: persistent grid (2 CTAs per SM), a block tile is 1024
 // consecutive slots, a warp tile 128, and lane L owns slots 4L..4L+3 of its warp
-// tile.  Warps are independent: there is no block-wide barrier inside the loop.
-// Per warp tile:
+// tile.  Warps are independent: there is no block-wide barrier inside the loop,
+// and warp tiles are not bound to warps -- every warp draws its next tile from a
+// work counter (global ones for flat frames and batched worlds, a per-CTA one for
+// hierarchy levels; see the level loop), which removed the long tail the fixed
+// tile = blockIdx + k * grid mapping ended a launch with.  Per warp tile:
 //
 //  * input: ONE cp.async.bulk (TMA, SASS UBLKCP) of the tile record (5632 or
 //    6144 B, kernels_transform.cuh) into the warp's shared buffer, completion on
