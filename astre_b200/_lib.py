@@ -45,6 +45,7 @@ SIGNATURES = {
     "astre_gpu_set_views": (C.c_int, [_P, C.c_uint32, _F, _U8]),
     "astre_gpu_set_world_views": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _F, _U8]),
     "astre_gpu_frame": (C.c_int, [_P, C.c_uint32, _P]),
+    "astre_gpu_sort": (C.c_int, [_P, _P]),
     "astre_gpu_sync": (C.c_int, [_P]),
     "astre_gpu_set_stream": (C.c_int, [_P, _P]),
     "astre_gpu_launch_count": (C.c_uint64, [_P]),

@@ -118,6 +118,9 @@ struct astre_gpu_ctx {
     // cached read-backs of the last frame
     bool frame_done = false, results_cached = false, results_cached_total_valid = false;
     uint32_t last_flags = 0, last_sort_passes = 0;
+    bool sort_pending = false;            // frame ran with ASTRE_FRAME_SORT_LATER: astre_gpu_sort still to come
+    SortPlan pending_plan{};
+    uint32_t pending_low_live_bits = 0;
     std::vector<uint32_t> h_counts;
     std::vector<unsigned long long> h_offsets;
     unsigned long long h_total = 0;
@@ -693,6 +696,48 @@ int astre_gpu_set_views(astre_gpu_ctx *ctx, uint32_t n_views, const float *clip1
     return astre_gpu_set_world_views(ctx, 1, 0, n_views, clip16, phase_mask);
 }
 
+// scan of the digit histograms + one pass per digit (+ tie fix-up): the sort of the frame's keys
+static int launch_sort(astre_gpu_ctx *ctx, const SortPlan &plan, uint32_t low_live_bits, cudaStream_t s)
+{
+    if (!(plan.n_passes || (ctx->sort_ties && low_live_bits))) return ASTRE_OK;
+    const uint32_t sort_grid = (uint32_t)ctx->sort_grid;   // co-resident CTAs only (static tile striding)
+    // programmatic dependent launch: each kernel of the chain is made resident while its predecessor drains
+    // and blocks in cudaGridDependencySynchronize() -- hides the launch latency between the short sort kernels
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+    cfg.gridDim = dim3(std::max(plan.n_passes, 1u)); cfg.blockDim = dim3(1024);   // block 0 also publishes the key count
+    const unsigned long long cap = ctx->max_keys;
+    CK(cudaLaunchKernelEx(&cfg, k_sort_scan, ctx->d_sc, (const uint32_t *)ctx->d_block_hist, ctx->hist_regions,
+                          (const FrameControl *)ctx->d_ctl, cap));
+    CK_LAUNCH();
+    for (int p = 0; p < (int)plan.n_passes; ++p) {
+        cfg.gridDim = dim3(sort_grid);
+        if (ctx->sort_threads == 256) {
+            cfg.blockDim = dim3(256);
+            CK(cudaLaunchKernelEx(&cfg, k_sort_pass<256, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
+        } else {
+            cfg.blockDim = dim3(1024);
+            CK(cudaLaunchKernelEx(&cfg, k_sort_pass<1024, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
+        }
+        CK_LAUNCH();
+    }
+    if (ctx->sort_ties && low_live_bits) {
+        const uint32_t low_bits = 26u - ctx->world_bits;           // width of the local-slot field
+        cfg.gridDim = dim3(sort_grid); cfg.blockDim = dim3(256);
+        CK(cudaLaunchKernelEx(&cfg, k_sort_ties_short, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
+                              ctx->d_long_runs, ctx->cap_long_runs));
+        CK_LAUNCH();
+        cfg.gridDim = dim3((unsigned)ctx->sm_count * 2);
+        CK(cudaLaunchKernelEx(&cfg, k_sort_ties_long, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
+                              low_live_bits, (const uint32_t *)ctx->d_long_runs, ctx->cap_long_runs));
+        CK_LAUNCH();
+    }
+    return ASTRE_OK;
+}
+
 int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 {
     if (!ctx) return ASTRE_ERR_INVALID;
@@ -701,7 +746,8 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     const uint32_t n = ctx->n_entities;
     const bool cull = (stage_flags & ASTRE_FRAME_CULL) && ctx->views_per_world > 0;
-    const bool sort = cull && (stage_flags & ASTRE_FRAME_SORT);
+    const bool sort_now = cull && (stage_flags & ASTRE_FRAME_SORT);
+    const bool sort = cull && (stage_flags & (ASTRE_FRAME_SORT | ASTRE_FRAME_SORT_LATER));   // plan + digit histograms
     const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
     if (ctx->n_worlds > 1 && (uint64_t)ctx->n_worlds * ctx->entities_per_world < n)
         return fail(ctx, ASTRE_ERR_STATE, "entity count %u exceeds n_worlds*entities_per_world", n);
@@ -810,44 +856,11 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         }
     }
 
-    if (sort && (plan.n_passes || (ctx->sort_ties && low_live_bits))) {
-        const uint32_t sort_grid = (uint32_t)ctx->sort_grid;   // co-resident CTAs only (static tile striding)
-        // programmatic dependent launch: each kernel of the chain is made resident while its predecessor drains
-        // and blocks in cudaGridDependencySynchronize() -- hides the launch latency between the short sort kernels
-        cudaLaunchAttribute pdl;
-        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
-        cudaLaunchConfig_t cfg{};
-        cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
-        cfg.gridDim = dim3(std::max(plan.n_passes, 1u)); cfg.blockDim = dim3(1024);   // block 0 also publishes the key count
-        const unsigned long long cap = ctx->max_keys;
-        CK(cudaLaunchKernelEx(&cfg, k_sort_scan, ctx->d_sc, (const uint32_t *)ctx->d_block_hist, ctx->hist_regions,
-                              (const FrameControl *)ctx->d_ctl, cap));
-        CK_LAUNCH();
-        for (int p = 0; p < (int)plan.n_passes; ++p) {
-            cfg.gridDim = dim3(sort_grid);
-            if (ctx->sort_threads == 256) {
-                cfg.blockDim = dim3(256);
-                CK(cudaLaunchKernelEx(&cfg, k_sort_pass<256, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
-            } else {
-                cfg.blockDim = dim3(1024);
-                CK(cudaLaunchKernelEx(&cfg, k_sort_pass<1024, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
-            }
-            CK_LAUNCH();
-        }
-        if (ctx->sort_ties && low_live_bits) {
-            const uint32_t low_bits = 26u - ctx->world_bits;           // width of the local-slot field
-            cfg.gridDim = dim3(sort_grid); cfg.blockDim = dim3(256);
-            CK(cudaLaunchKernelEx(&cfg, k_sort_ties_short, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
-                                  ctx->d_long_runs, ctx->cap_long_runs));
-            CK_LAUNCH();
-            cfg.gridDim = dim3((unsigned)ctx->sm_count * 2);
-            CK(cudaLaunchKernelEx(&cfg, k_sort_ties_long, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
-                                  low_live_bits, (const uint32_t *)ctx->d_long_runs, ctx->cap_long_runs));
-            CK_LAUNCH();
-        }
-    }
-    ctx->last_sort_passes = sort ? plan.n_passes : 0u;
+    if (sort_now) { if (int rc = launch_sort(ctx, plan, low_live_bits, s)) return rc; }
+    ctx->sort_pending = sort && !sort_now;
+    ctx->pending_plan = plan;
+    ctx->pending_low_live_bits = low_live_bits;
+    ctx->last_sort_passes = sort_now ? plan.n_passes : 0u;
     if (n_counts) {
         cudaLaunchAttribute pdl;
         pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -861,6 +874,23 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     ctx->frame_done = true;
     ctx->results_cached = false;
     ctx->last_flags = stage_flags;
+    ctx->last_stream = s;
+    return ASTRE_OK;
+}
+
+int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done || !ctx->sort_pending)
+        return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_sort needs a frame run with ASTRE_FRAME_CULL | ASTRE_FRAME_SORT_LATER");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    if (int rc = launch_sort(ctx, ctx->pending_plan, ctx->pending_low_live_bits, s)) return rc;
+    ctx->last_sort_passes = ctx->pending_plan.n_passes;
+    ctx->last_flags = (ctx->last_flags & ~(uint32_t)ASTRE_FRAME_SORT_LATER) | ASTRE_FRAME_SORT;
+    ctx->sort_pending = false;
+    ctx->results_cached = false;
+    CK(cudaEventRecord(ctx->ev_end, s));
     ctx->last_stream = s;
     return ASTRE_OK;
 }

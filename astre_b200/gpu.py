@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import AstreError, DrawRun, MeshBounds, load_library
 
-FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS = 1, 2, 4, 8
+FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER = 1, 2, 4, 8, 16
 FRAME_ALL = 7
 
 PHASE_OPAQUE, PHASE_TRANSPARENT, PHASE_SHADOW_CASTER, PHASE_DEBUG = 1, 2, 4, 8
@@ -125,6 +125,10 @@ class GpuContext:
     # -- frame --
     def frame(self, flags=FRAME_ALL, stream=None):
         self._check(self._lib.astre_gpu_frame(self._h, int(flags), C.c_void_p(stream) if stream else None))
+
+    def sort(self, stream=None):
+        """Sort the keys of a frame that ran with FRAME_CULL | FRAME_SORT_LATER (lets the count exchange overlap the sort)."""
+        self._check(self._lib.astre_gpu_sort(self._h, stream))
 
     def sync(self):
         self._check(self._lib.astre_gpu_sync(self._h))

@@ -236,11 +236,22 @@ def main():
         __cuda_array_interface__ = {"shape": (F,), "typestr": "<i4", "data": (ctx.device_counts_ptr(), False), "version": 2}
     counts_dev = torch.as_tensor(_DeviceCounts(), device="cuda")
 
+    side = torch.cuda.Stream() if world > 1 else None
+    cull_done = torch.cuda.Event() if world > 1 else None
+
     def step():
-        ctx.frame(gpu.FRAME_ALL)
-        if world > 1:
-            # per-shard visible counts -> every rank: the only exchange on the path (NCCL all-gather)
+        if world == 1:
+            ctx.frame(gpu.FRAME_ALL)
+            return
+        # The per-view counts are final when the cull kernel ends: the only exchange on the path (NCCL all-gather of
+        # the per-shard counts) runs on a side stream while the main stream sorts this shard's keys.
+        ctx.frame(gpu.FRAME_TRANSFORM | gpu.FRAME_CULL | gpu.FRAME_SORT_LATER)
+        cull_done.record(stream)
+        side.wait_event(cull_done)
+        with torch.cuda.stream(side):
             multi.exchange_counts(counts_dev)
+        ctx.sort()
+        stream.wait_stream(side)
 
     def barrier():
         if world > 1:

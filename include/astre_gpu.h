@@ -71,6 +71,7 @@ enum {
     ASTRE_FRAME_CULL      = 1u << 1,  /* frustum test + compaction + key emission            */
     ASTRE_FRAME_SORT      = 1u << 2,  /* device radix sort of the emitted keys               */
     ASTRE_FRAME_BASIS     = 1u << 3,  /* forward/up/right of every entity                    */
+    ASTRE_FRAME_SORT_LATER = 1u << 4, /* prepare the sort (digit histograms) but run it in astre_gpu_sort */
     ASTRE_FRAME_ALL       = 7u
 };
 
@@ -162,6 +163,11 @@ ASTRE_API int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, u
  * Asynchronous; results are read with the astre_gpu_read_* calls, which
  * synchronise. */
 ASTRE_API int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream);
+/* Sorts the keys of the last frame, which must have run with ASTRE_FRAME_CULL |
+ * ASTRE_FRAME_SORT_LATER.  Splitting the frame lets a caller start work that only
+ * needs the per-view counts -- the multi-GPU count exchange -- while
+ * the sort runs.  Afterwards the frame reads exactly like one run with ASTRE_FRAME_SORT. */
+ASTRE_API int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream);
 ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
 /* Makes every later call on ctx (mirror updates, frames with stream == NULL,
  * read-backs) enqueue on the caller's cudaStream_t instead of the context's own

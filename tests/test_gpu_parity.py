@@ -344,6 +344,27 @@ def test_sort_ties_long_runs(oracle, ties, monkeypatch):
     assert n_keys > 80_000
 
 
+def test_deferred_sort_equals_one_call(oracle):
+    """frame(CULL | SORT_LATER) + sort() reads exactly like frame(ALL); before sort() the keys are there, unsorted."""
+    s = scenes.config3(300_000)
+    _, o_keys, o_counts = oracle.frame(s)
+    with GpuContext(s.n, max_views=s.views_per_world) as ctx:
+        scenes.load_into(ctx, s)
+        for _ in range(2):
+            ctx.frame(gpu.FRAME_TRANSFORM | gpu.FRAME_CULL | gpu.FRAME_SORT_LATER)
+            assert np.array_equal(ctx.read_counts(), o_counts)
+            assert np.array_equal(np.sort(ctx.read_all_keys()), o_keys)
+            with pytest.raises(AstreError):
+                ctx.read_keys(0)                       # per-view lists need the sort
+            ctx.sort()
+            assert np.array_equal(ctx.read_all_keys(), o_keys)
+            assert np.array_equal(np.concatenate([ctx.read_keys(v) for v in range(s.views_per_world)]), o_keys)
+            with pytest.raises(AstreError):
+                ctx.sort()                             # nothing pending any more
+        ctx.frame()
+        assert np.array_equal(ctx.read_all_keys(), o_keys)
+
+
 def _random_scene(rng, i):
     """A small adversarial scene: random size, view count, cameras (perspective, orthographic, degenerate),
     masks, flags, optional parent forest, a sprinkle of special float values, random mesh bounds."""
