@@ -1,0 +1,3 @@
+// Part of the GLM-API stand-in; see refglm.hpp. TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <glm/refglm.hpp>

@@ -46,7 +46,8 @@ def test_product_never_touches_the_oracle():
     """A product path that routes through the oracle voids every parity claim: nothing
     under astre_b200/ may import, link or execute anything under oracle/ or tests/."""
     pkg = os.path.join(ROOT, "astre_b200")
-    banned = ("oracle_lib", "astre_oracle", "libastre_oracle", "oracle/", "orc_", "np_reference", "refstore")
+    banned = ("oracle_lib", "astre_oracle", "libastre_oracle", "oracle/", "orc_", "np_reference", "refstore",
+              "libastre_ref", "ref_lib", "_ref/", "ref_world_", "refglm")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")) or f == "Makefile":
@@ -54,4 +55,4 @@ def test_product_never_touches_the_oracle():
                 for b in banned:
                     assert b not in text, (os.path.join(dirpath, f), b)
     out = subprocess.run(["ldd", astre_b200.library_path()], capture_output=True, text=True).stdout
-    assert "oracle" not in out
+    assert "oracle" not in out and "astre_ref" not in out

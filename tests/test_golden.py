@@ -84,3 +84,67 @@ def test_config1_on_gpu_matches_fixture():
         world, keys, counts = ctx.read_world(0, s.n), ctx.read_all_keys(), ctx.read_counts()
     assert np.array_equal(world.view(np.uint32), unhex(d["world"], (s.n, 16)).view(np.uint32))
     assert [f"{int(k):016x}" for k in keys] == d["keys"] and counts.tolist() == d["counts"]
+
+
+# ---- vectors computed by the reference's own sources (tests/golden/make_ref_fixtures.py, oracle/_ref) ---------
+
+def unhexs(s, shape):
+    """string of 8-hex-digit float32 bit patterns -> array"""
+    return np.array([int(s[i:i + 8], 16) for i in range(0, len(s), 8)], np.uint32).view(np.float32).reshape(shape)
+
+
+def _same(a, b):
+    import oracle_lib
+    return np.array_equal(oracle_lib.bits(a), oracle_lib.bits(b))
+
+
+def test_ref_fixture_transform_oracle(oracle):
+    t = load("ref_fixture.json")["transform"]
+    n = t["n"]
+    pos, rot, scl = unhexs(t["pos"], (n, 3)), unhexs(t["rot"], (n, 4)), unhexs(t["scale"], (n, 3))
+    world, f, u, r = oracle.transform_flat(pos, rot, scl, basis=True)
+    assert _same(world, unhexs(t["world"], (n, 16)))
+    assert _same(f, unhexs(t["forward"], (n, 3))) and _same(u, unhexs(t["up"], (n, 3))) and _same(r, unhexs(t["right"], (n, 3)))
+
+
+def test_ref_fixture_camera_and_lights_oracle_and_host_math(oracle, gpu_lib):
+    """The oracle AND the product's host-side view builders (astre_camera_matrices / astre_light_space_matrix:
+    plain C++, no device needed) reproduce the matrices the reference's CameraSystem / calculateLightSpaceMatrices
+    computed."""
+    d = load("ref_fixture.json")
+    for c in d["camera"]:
+        pos, fwd, up = unhexs(c["pos"], 3), unhexs(c["forward"], 3), unhexs(c["up"], 3)
+        view, proj = unhexs(c["view"], 16), unhexs(c["proj"], 16)
+        oview, oproj = oracle.camera_view_proj(pos, fwd, up, c["fov"], c["aspect"], c["near"], c["far"])
+        assert _same(oview, view) and _same(oproj, proj)
+        pview, pproj, pclip = gpu.camera_matrices(pos, fwd, up, c["fov"], c["aspect"], c["near"], c["far"])
+        assert _same(pview, view) and _same(pproj, proj) and _same(pclip, oracle.mat4_mul(proj, view))
+    for l in d["lights"]:
+        pos, direction, want = unhexs(l["position"], 3), unhexs(l["direction"], 3), unhexs(l["light_space"], 16)
+        assert _same(oracle.light_space(pos, direction, l["type"], l["outer_cutoff"]), want), l
+        assert _same(gpu.light_space_matrix(pos, direction, l["type"], l["outer_cutoff"]), want), l
+
+
+def test_ref_fixture_interpolate_oracle(oracle):
+    t = load("ref_fixture.json")["interpolate"]
+    n = t["n"]
+    a = tuple(unhexs(t[k], (n, w)) for k, w in (("pos_a", 3), ("rot_a", 4), ("scale_a", 3)))
+    b = tuple(unhexs(t[k], (n, w)) for k, w in (("pos_b", 3), ("rot_b", 4), ("scale_b", 3)))
+    for fr in t["frames"]:
+        assert _same(oracle.interpolate(fr["alpha"], a, b), unhexs(fr["model"], (n, 16))), fr["alpha"]
+
+
+@pytest.mark.gpu
+def test_ref_fixture_transform_on_gpu():
+    """The CUDA path reproduces what the reference's TransformSystem::run computed -- no oracle involved."""
+    t = load("ref_fixture.json")["transform"]
+    n = t["n"]
+    pos, rot, scl = unhexs(t["pos"], (n, 3)), unhexs(t["rot"], (n, 4)), unhexs(t["scale"], (n, 3))
+    with gpu.GpuContext(n, max_views=1) as ctx:
+        ctx.upload_entities(0, pos, rot, scl)
+        ctx.set_entity_count(n)
+        ctx.frame(gpu.FRAME_TRANSFORM | gpu.FRAME_BASIS)
+        world = ctx.read_world(0, n)
+        f, u, r = ctx.read_basis(0, n)
+    assert _same(world, unhexs(t["world"], (n, 16)))
+    assert _same(f, unhexs(t["forward"], (n, 3))) and _same(u, unhexs(t["up"], (n, 3))) and _same(r, unhexs(t["right"], (n, 3)))

@@ -218,3 +218,23 @@ def test_reference_layout_baseline_matches_oracle(oracle):
             assert np.array_equal(oracle_lib.bits(m), oracle_lib.bits(ref[i]))
     finally:
         lib.refstore_destroy(C.c_void_p(st))
+
+
+def test_trs_matrix_conventions_against_scipy(oracle):
+    """Tolerance-level check of the conventions (not of the bits): quaternion order x,y,z,w, right-handed active
+    rotation, column-major storage, M = T * R * S -- against scipy's independent Rotation class."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        p, s = rng.uniform(-50, 50, 3), rng.uniform(0.2, 4, 3)
+        m = oracle.trs_matrix(p, q, s).reshape(4, 4).T               # column-major -> math layout [row, col]
+        want = np.eye(4)
+        want[:3, :3] = Rotation.from_quat(q).as_matrix() @ np.diag(s)
+        want[:3, 3] = p
+        assert np.allclose(m, want, rtol=0, atol=2e-5)
+        f, u, r = oracle.basis(q.astype(np.float32))
+        rot = Rotation.from_quat(q)
+        assert np.allclose(f, rot.apply([0, 0, -1]), atol=1e-6) and np.allclose(u, rot.apply([0, 1, 0]), atol=1e-6)
+        assert np.allclose(r, rot.apply([1, 0, 0]), atol=1e-6)
