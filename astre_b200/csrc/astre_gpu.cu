@@ -63,21 +63,22 @@ struct astre_gpu_ctx {
     uint32_t cap_counts = 0;
     FrameControl *d_ctl = nullptr;
     SortControl *d_sc = nullptr;
-    uint32_t *d_long_runs = nullptr;      // starts of tie runs longer than kShortRun (sort)
-    uint32_t cap_long_runs = 0;
-    bool sort_ties = false;               // ASTRE_SORT_TIES=1: radix passes over the bits above the slot field + tie fix-up
-                                          // (measured r1: 0.434 vs 0.441 ms on config 3, but 0.78 vs 0.55 ms on a dense scene)
-    uint32_t *d_block_hist = nullptr;     // [hist_regions][8][256] partial digit histograms
-    uint32_t hist_regions = 0;
+    uint32_t *d_bins = nullptr;           // key sort: bucket counts -> bucket starts -> bucket ends (kernels_sort.cuh)
+    uint32_t cap_bin_bits = 0;            // log2 of the bins allocated
+    uint32_t *d_chunk_first = nullptr;    // key sort: first bucket of every 1024-key chunk
+    unsigned long long *h_hint = nullptr; // mapped host word: key total of the last finished frame (sizes the next frame's buckets)
+    unsigned long long *d_hint = nullptr;
+    uint32_t force_lsd = 0;               // ASTRE_SORT_FORCE_LSD=1: always take the LSD fallback (tests)
+    int bin_bits_override = -1;           // ASTRE_SORT_BIN_BITS=n: fixed bucket-digit width (tests)
     uint32_t claim_groups = 8;            // work counters of the fused kernel in a flat frame (ASTRE_CLAIM_GROUPS; 0 = per-CTA shared counters)
     uint32_t shader_or = 0;               // OR of every shader id uploaded (live bits of the key's shader field)
-    int sort_threads = 256;               // CTA size of k_sort_pass (ASTRE_SORT_THREADS = 256 | 1024), 8 keys per thread
-    int sort_grid = 148;                  // co-resident CTAs of k_sort_pass
+    int sort_grid = 148;                  // co-resident CTAs of k_sort_lsd_all
     unsigned long long *d_lookback = nullptr;
     float4 *d_gather = nullptr;
     uint64_t cap_gather = 0;
-    uint2 *d_heads = nullptr;            // draw-run heads (f2), then one counter word
+    RunHead *d_heads = nullptr;          // draw-run heads (f2), in list order
     uint32_t cap_heads = 0;
+    uint32_t *d_head_counts = nullptr;   // run heads per CTA of k_run_count, then their exclusive scan (+ total)
     uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
     uint32_t epoch = 0;
 
@@ -117,10 +118,11 @@ struct astre_gpu_ctx {
 
     // cached read-backs of the last frame
     bool frame_done = false, results_cached = false, results_cached_total_valid = false;
-    uint32_t last_flags = 0, last_sort_passes = 0;
+    uint32_t last_flags = 0;
+    bool last_sorted = false;             // the last frame's keys went through the sort
     bool sort_pending = false;            // frame ran with ASTRE_FRAME_SORT_LATER: astre_gpu_sort still to come
     SortPlan pending_plan{};
-    uint32_t pending_low_live_bits = 0;
+    BinPlan pending_bins{};
     std::vector<uint32_t> h_counts;
     std::vector<unsigned long long> h_offsets;
     unsigned long long h_total = 0;
@@ -181,8 +183,7 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     P.keys = c->d_keys[0];
     P.counts = c->d_counts;
     P.ctl = c->d_ctl;
-    P.block_hist = c->d_block_hist;
-    P.hist_regions = c->hist_regions;
+    P.bins = c->d_bins;
     P.claim_groups = c->claim_groups;
     P.key_cap = c->max_keys;
     P.n_meshes = c->n_meshes;
@@ -195,17 +196,20 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
 }
 
 __global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts, uint32_t epoch,
-                              uint32_t *block_hist, uint32_t n_hist_words)
+                              uint32_t *bins, uint32_t n_bins)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         ctl->key_total = 0; ctl->overflow = 0; ctl->barrier = 0;
         sc->n_keys = 0; sc->epoch = epoch;
+        sc->max_bucket = 0; sc->scan_ticket = 0; sc->sum_sq = 0; sc->lsd_barrier = 0; sc->result_buf = 0; sc->path = kSortNone;
     }
-    if (tid < kSortPasses) sc->skip[tid] = 1;
+    if (tid < kSortPasses) { sc->skip[tid] = 1; sc->tile_counter[tid] = 0; }
+    for (uint32_t i = tid; i < (uint32_t)(kSortPasses * 256); i += nth) (&sc->hist[0][0])[i] = 0;
     for (uint32_t i = tid; i < (uint32_t)(kClaimGroups * kClaimStride); i += nth) ctl->claim[i] = 0;
     for (uint32_t i = tid; i < n_counts; i += nth) counts[i] = 0;
-    for (uint32_t i = tid; i < n_hist_words; i += nth) block_hist[i] = 0;
+    uint4 *bins4 = reinterpret_cast<uint4 *>(bins);
+    for (uint32_t i = tid; i < (n_bins >> 2); i += nth) bins4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Depth of every slot; returns the level count or -1 (bad index / cycle).
@@ -299,11 +303,8 @@ int cache_results(astre_gpu_ctx *ctx)
     CK(cudaStreamSynchronize(s));
     CK(cudaMemcpy(&ctl, ctx->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
     uint32_t result_buf = 0;
-    if (ctx->last_sort_passes) {   // the sorted keys are in buffer (number of digit passes that were not skipped) & 1
-        uint32_t skip[kSortPasses];
-        CK(cudaMemcpy(skip, ctx->d_sc->skip, sizeof skip, cudaMemcpyDeviceToHost));
-        for (uint32_t p = 0; p < ctx->last_sort_passes; ++p) result_buf ^= skip[p] ? 0u : 1u;
-    }
+    if (ctx->last_sorted)          // which key buffer the sort ended in is decided on the device
+        CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof result_buf, cudaMemcpyDeviceToHost));
     ctx->h_counts.assign(n_counts, 0);
     ctx->h_offsets.assign((size_t)n_counts + 1, 0);
     if (n_counts) {
@@ -409,21 +410,21 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
     CKC(cudaMalloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
     CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
-    ctx->cap_long_runs = (uint32_t)std::min<uint64_t>(ctx->max_keys / kShortRun + 1, 1u << 22);
-    CKC(cudaMalloc(&ctx->d_long_runs, (size_t)ctx->cap_long_runs * sizeof(uint32_t)));
-    if (std::getenv("ASTRE_SORT_TIES")) ctx->sort_ties = true;
     if (const char *m = std::getenv("ASTRE_CLAIM_GROUPS")) ctx->claim_groups = (uint32_t)std::max(std::atoi(m), 0);
-    // partial sort histograms: CTAs of the fused kernel add (RED) into region blockIdx % 8.  Measured on config 3:
-    // 296 regions (one per CTA) 0.4447 ms per frame, 32: 0.4371, 8: 0.4357, 1: 0.4369 -- fewer words to clear and to sum.
-    ctx->hist_regions = 8u;
-    if (const char *m = std::getenv("ASTRE_HIST_REGIONS")) ctx->hist_regions = std::max(1, std::min(std::atoi(m), ctx->sm_count * 2));
-    CKC(cudaMalloc(&ctx->d_block_hist, (size_t)ctx->hist_regions * kHistWords * sizeof(uint32_t)));
-    if (const char *m = std::getenv("ASTRE_SORT_THREADS")) ctx->sort_threads = std::atoi(m) == 1024 ? 1024 : 256;
+    // key sort: buckets of ~4-8 keys -> up to max_keys / 4 bins (between 2^8 and 2^22)
+    ctx->cap_bin_bits = kMinBinBits;
+    while (ctx->cap_bin_bits < kMaxBinBits && (1ull << ctx->cap_bin_bits) * 4ull < ctx->max_keys) ++ctx->cap_bin_bits;
+    CKC(cudaMalloc(&ctx->d_bins, (size_t)(1u << ctx->cap_bin_bits) * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_chunk_first, (size_t)(ctx->max_keys / kChunkKeys + 2) * sizeof(uint32_t)));
+    CKC(cudaHostAlloc(&ctx->h_hint, sizeof(unsigned long long), cudaHostAllocMapped));
+    *ctx->h_hint = ~0ull;                                            // no frame has finished yet
+    CKC(cudaHostGetDevicePointer(&ctx->d_hint, ctx->h_hint, 0));
+    if (std::getenv("ASTRE_SORT_FORCE_LSD")) ctx->force_lsd = 1u;
+    if (const char *m = std::getenv("ASTRE_SORT_BIN_BITS")) ctx->bin_bits_override = std::atoi(m);
     {
         int occ_sort = 0;
-        if (ctx->sort_threads == 256) CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_pass<256, 8>, 256, 0));
-        else CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_pass<1024, 8>, 1024, 0));
-        ctx->sort_grid = ctx->sm_count * std::max(occ_sort, 1);
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_lsd_all, kSortThreads, 0));
+        ctx->sort_grid = ctx->sm_count * std::max(occ_sort, 1);     // co-resident: the fallback has grid barriers
     }
     CKC(cudaEventCreate(&ctx->ev_begin));
     CKC(cudaEventCreate(&ctx->ev_cull0));
@@ -467,7 +468,8 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_block_hist, ctx->d_heads, ctx->d_long_runs,
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_bins, ctx->d_chunk_first, ctx->d_heads,
+                     ctx->d_head_counts,
                      ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -480,6 +482,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h_hint) cudaFreeHost(ctx->h_hint);
     delete ctx;
 }
 
@@ -696,45 +699,35 @@ int astre_gpu_set_views(astre_gpu_ctx *ctx, uint32_t n_views, const float *clip1
     return astre_gpu_set_world_views(ctx, 1, 0, n_views, clip16, phase_mask);
 }
 
-// scan of the digit histograms + one pass per digit (+ tie fix-up): the sort of the frame's keys
-static int launch_sort(astre_gpu_ctx *ctx, const SortPlan &plan, uint32_t low_live_bits, cudaStream_t s)
+// The sort of the frame's keys: bin scan -> scatter -> rank, then the LSD fallback, which returns at once unless
+// the scan found the buckets too crowded (all decided on the device).  Programmatic dependent launch: each kernel of
+// the chain is made resident while its predecessor drains and blocks in cudaGridDependencySynchronize().
+static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &plan, cudaStream_t s)
 {
-    if (!(plan.n_passes || (ctx->sort_ties && low_live_bits))) return ASTRE_OK;
-    const uint32_t sort_grid = (uint32_t)ctx->sort_grid;   // co-resident CTAs only (static tile striding)
-    // programmatic dependent launch: each kernel of the chain is made resident while its predecessor drains
-    // and blocks in cudaGridDependencySynchronize() -- hides the launch latency between the short sort kernels
+    if (!bp.bits) return ASTRE_OK;                 // no key bit can differ: at most one key
     cudaLaunchAttribute pdl;
     pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
     cudaLaunchConfig_t cfg{};
     cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
-    cfg.gridDim = dim3(std::max(plan.n_passes, 1u)); cfg.blockDim = dim3(1024);   // block 0 also publishes the key count
     const unsigned long long cap = ctx->max_keys;
-    CK(cudaLaunchKernelEx(&cfg, k_sort_scan, ctx->d_sc, (const uint32_t *)ctx->d_block_hist, ctx->hist_regions,
-                          (const FrameControl *)ctx->d_ctl, cap));
+    const uint32_t n_bins = 1u << bp.bits;
+    const FrameControl *ctl = ctx->d_ctl;
+    const uint32_t wide = (uint32_t)ctx->sm_count * 4u;
+    cfg.gridDim = dim3(std::max(n_bins / kScanTile, 1u)); cfg.blockDim = dim3(1024);
+    CK(cudaLaunchKernelEx(&cfg, k_bin_scan, ctx->d_bins, n_bins, ctx->d_sc, ctx->d_chunk_first));
     CK_LAUNCH();
-    for (int p = 0; p < (int)plan.n_passes; ++p) {
-        cfg.gridDim = dim3(sort_grid);
-        if (ctx->sort_threads == 256) {
-            cfg.blockDim = dim3(256);
-            CK(cudaLaunchKernelEx(&cfg, k_sort_pass<256, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
-        } else {
-            cfg.blockDim = dim3(1024);
-            CK(cudaLaunchKernelEx(&cfg, k_sort_pass<1024, 8>, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, p));
-        }
-        CK_LAUNCH();
-    }
-    if (ctx->sort_ties && low_live_bits) {
-        const uint32_t low_bits = 26u - ctx->world_bits;           // width of the local-slot field
-        cfg.gridDim = dim3(sort_grid); cfg.blockDim = dim3(256);
-        CK(cudaLaunchKernelEx(&cfg, k_sort_ties_short, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
-                              ctx->d_long_runs, ctx->cap_long_runs));
-        CK_LAUNCH();
-        cfg.gridDim = dim3((unsigned)ctx->sm_count * 2);
-        CK(cudaLaunchKernelEx(&cfg, k_sort_ties_long, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, plan.n_passes, low_bits,
-                              low_live_bits, (const uint32_t *)ctx->d_long_runs, ctx->cap_long_runs));
-        CK_LAUNCH();
-    }
+    cfg.gridDim = dim3(wide); cfg.blockDim = dim3(256);
+    CK(cudaLaunchKernelEx(&cfg, k_bin_scatter, (const unsigned long long *)ctx->d_keys[0], ctx->d_keys[1], ctx->d_bins, bp,
+                          (const SortControl *)ctx->d_sc, ctl, cap, ctx->force_lsd));
+    CK_LAUNCH();
+    CK(cudaLaunchKernelEx(&cfg, k_bin_rank, (const unsigned long long *)ctx->d_keys[1], ctx->d_keys[0], (const uint32_t *)ctx->d_bins,
+                          (const uint32_t *)ctx->d_chunk_first, bp, ctx->d_sc, ctl, cap, ctx->force_lsd));
+    CK_LAUNCH();
+    cfg.gridDim = dim3((unsigned)ctx->sort_grid); cfg.blockDim = dim3(kSortThreads);
+    CK(cudaLaunchKernelEx(&cfg, k_sort_lsd_all, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, ctl, cap,
+                          ctx->force_lsd));
+    CK_LAUNCH();
     return ASTRE_OK;
 }
 
@@ -761,24 +754,33 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     CK(cudaEventRecord(ctx->ev_begin, s));
     // digit plan of the sort from the key fields in use (all other key bits are zero in every key)
     SortPlan plan;
+    BinPlan bp;
     std::memset(&plan, 0, sizeof plan);
-    uint32_t low_live_bits = 0;
+    std::memset(&bp, 0, sizeof bp);
     if (sort) {
         auto bits_for = [](uint64_t max_value) { uint32_t b = 0; while (b < 32 && (max_value >> b)) ++b; return b; };
         const uint32_t wb = ctx->world_bits;
         const uint64_t local_max = (ctx->n_worlds > 1 ? ctx->entities_per_world : n) ? (uint64_t)(ctx->n_worlds > 1 ? ctx->entities_per_world : n) - 1 : 0;
-        unsigned long long live = 0;
-        low_live_bits = bits_for(local_max);
-        if (!ctx->sort_ties) live |= ((1ull << low_live_bits) - 1ull);     // else: the slot field is ordered by the tie fix-up
+        unsigned long long live = (1ull << bits_for(local_max)) - 1ull;
         live |= ((1ull << 14) - 1ull) << (26 - wb);
         live |= ((1ull << bits_for(ctx->n_meshes ? ctx->n_meshes - 1 : 0)) - 1ull) << (40 - wb);
         live |= (unsigned long long)ctx->shader_or << (51 - wb);
         live |= ((1ull << bits_for(ctx->views_per_world ? ctx->views_per_world - 1 : 0)) - 1ull) << (59 - wb);
         if (wb) live |= ((1ull << wb) - 1ull) << (64 - wb);
         plan = make_sort_plan(live);
+        // buckets of ~4-8 keys: one bin per 4 keys of the last frame that finished (a hint -- any width sorts correctly;
+        // before the first frame: one key per 16 entity-view pairs)
+        const unsigned long long seen = *(volatile unsigned long long *)ctx->h_hint;
+        const unsigned long long expect = seen != ~0ull ? std::min<unsigned long long>(seen, ctx->max_keys)
+                                                        : (unsigned long long)n * ctx->views_per_world / 16ull;
+        uint32_t want = kMinBinBits;
+        while (want < ctx->cap_bin_bits && (1ull << want) * 4ull < expect) ++want;
+        if (ctx->bin_bits_override >= 0) want = std::min<uint32_t>((uint32_t)ctx->bin_bits_override, ctx->cap_bin_bits);
+        bp = make_bin_plan(live, want);
     }
-    const uint32_t n_hist_words = sort ? ctx->hist_regions * kHistWords : 0u;
-    k_frame_begin<<<64, 256, 0, s>>>(ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch, ctx->d_block_hist, n_hist_words);
+    const uint32_t n_bins = bp.bits ? (1u << bp.bits) : 0u;
+    k_frame_begin<<<std::max<uint32_t>(64u, std::min<uint32_t>(n_bins / 4096u, (uint32_t)ctx->sm_count * 4u)), 256, 0, s>>>(
+        ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch, ctx->d_bins, n_bins);
     CK_LAUNCH();
 
     const FrameParams P = params_of(ctx, cull);
@@ -801,7 +803,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             if (!cull) fn = hier ? (const void *)k_frame_fused<true, false, false> : (const void *)k_frame_fused<false, false, false>;
             else if (hier) fn = worlds ? (const void *)k_frame_fused<true, true, true> : (const void *)k_frame_fused<true, false, true>;
             else fn = worlds ? (const void *)k_frame_fused<false, true, true> : (const void *)k_frame_fused<false, false, true>;
-            void *args[] = { (void *)&P, (void *)&ctx->h_viewset, (void *)&plan, (void *)&LT };
+            void *args[] = { (void *)&P, (void *)&ctx->h_viewset, (void *)&bp, (void *)&LT };
             if (LT.n > 1) launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
             else launch_err = cudaLaunchKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
             barrier_rounds += (LT.n - 1) * g;
@@ -823,7 +825,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
                     const Level &L = ctx->levels[l];
                     const uint32_t grid = std::min<uint32_t>(ceil_div(L.count, kBlockThreads), (uint32_t)ctx->sm_count * 8);
                     k_transform_cull_indexed<<<grid, kBlockThreads, 0, s>>>(
-                        P, plan, L.contiguous ? nullptr : ctx->d_level_slots + L.list_offset, L.first, L.count);
+                        P, bp, L.contiguous ? nullptr : ctx->d_level_slots + L.list_offset, L.first, L.count);
                     CK_LAUNCH();
                     ++l;
                     continue;
@@ -856,18 +858,19 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         }
     }
 
-    if (sort_now) { if (int rc = launch_sort(ctx, plan, low_live_bits, s)) return rc; }
+    if (sort_now) { if (int rc = launch_sort(ctx, bp, plan, s)) return rc; }
     ctx->sort_pending = sort && !sort_now;
     ctx->pending_plan = plan;
-    ctx->pending_low_live_bits = low_live_bits;
-    ctx->last_sort_passes = sort_now ? plan.n_passes : 0u;
+    ctx->pending_bins = bp;
+    ctx->last_sorted = sort_now && bp.bits != 0;
     if (n_counts) {
         cudaLaunchAttribute pdl;
         pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
         cudaLaunchConfig_t cfg{};
         cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.gridDim = dim3(1); cfg.blockDim = dim3(256);
-        CK(cudaLaunchKernelEx(&cfg, k_scan_counts, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts));
+        CK(cudaLaunchKernelEx(&cfg, k_scan_counts, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts,
+                              (const FrameControl *)ctx->d_ctl, ctx->d_hint));
         CK_LAUNCH();
     }
     CK(cudaEventRecord(ctx->ev_end, s));
@@ -885,8 +888,8 @@ int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream)
         return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_sort needs a frame run with ASTRE_FRAME_CULL | ASTRE_FRAME_SORT_LATER");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (int rc = launch_sort(ctx, ctx->pending_plan, ctx->pending_low_live_bits, s)) return rc;
-    ctx->last_sort_passes = ctx->pending_plan.n_passes;
+    if (int rc = launch_sort(ctx, ctx->pending_bins, ctx->pending_plan, s)) return rc;
+    ctx->last_sorted = ctx->pending_bins.bits != 0;
     ctx->last_flags = (ctx->last_flags & ~(uint32_t)ASTRE_FRAME_SORT_LATER) | ASTRE_FRAME_SORT;
     ctx->sort_pending = false;
     ctx->results_cached = false;
@@ -970,31 +973,59 @@ int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, 
     const uint32_t n = (uint32_t)ctx->h_total;
     *n_out = 0;
     if (!n) return ASTRE_OK;
+    const uint32_t n_ctas = (uint32_t)ctx->sm_count * 8u;
     if (!ctx->d_heads) {
-        ctx->cap_heads = (uint32_t)std::min<uint64_t>(ctx->max_keys, 1u << 20);
-        CK(cudaMalloc(&ctx->d_heads, ((size_t)ctx->cap_heads + 1) * sizeof(uint2)));
+        ctx->cap_heads = (uint32_t)std::min<uint64_t>(ctx->max_keys, 1u << 22);
+        CK(cudaMalloc(&ctx->d_heads, (size_t)ctx->cap_heads * sizeof(RunHead)));
+        CK(cudaMalloc(&ctx->d_head_counts, ((size_t)n_ctas + 1) * sizeof(uint32_t)));
     }
     cudaStream_t s = ctx->last_stream;
-    uint32_t *counter = reinterpret_cast<uint32_t *>(ctx->d_heads + ctx->cap_heads);
-    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), s));
     const uint32_t class_shift = 40u - ctx->world_bits;   // below it: depth and slot
-    k_run_heads<<<std::min<uint32_t>(ceil_div(n, 256), (uint32_t)ctx->sm_count * 8), 256, 0, s>>>(
-        ctx->d_keys[ctx->h_result_buf], n, class_shift, ctx->d_heads, ctx->cap_heads, counter);
+    const uint32_t per_cta = ceil_div(n, n_ctas);
+    const unsigned long long *keys = ctx->d_keys[ctx->h_result_buf];
+    k_run_count<<<n_ctas, kRunThreads, 0, s>>>(keys, n, class_shift, per_cta, ctx->d_head_counts);
+    CK_LAUNCH();
+    k_run_scan<<<1, 1024, 0, s>>>(ctx->d_head_counts, n_ctas);
+    CK_LAUNCH();
+    k_run_write<<<n_ctas, kRunThreads, 0, s>>>(keys, n, class_shift, per_cta, ctx->d_head_counts, ctx->d_heads, ctx->cap_heads);
     CK_LAUNCH();
     uint32_t n_heads = 0;
-    CK(cudaMemcpyAsync(&n_heads, counter, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&n_heads, ctx->d_head_counts + n_ctas, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (n_heads > ctx->cap_heads) return fail(ctx, ASTRE_ERR_CAPACITY, "%u draw runs exceed the internal capacity %u", n_heads, ctx->cap_heads);
-    std::vector<uint2> heads(n_heads);
-    CK(cudaMemcpy(heads.data(), ctx->d_heads, (size_t)n_heads * sizeof(uint2), cudaMemcpyDeviceToHost));
-    std::sort(heads.begin(), heads.end(), [](const uint2 &a, const uint2 &b) { return a.x < b.x; });
+    std::vector<RunHead> heads(n_heads);
+    CK(cudaMemcpy(heads.data(), ctx->d_heads, (size_t)n_heads * sizeof(RunHead), cudaMemcpyDeviceToHost));
     *n_out = n_heads;
-    for (uint32_t i = 0; i < n_heads && i < cap; ++i) {
-        runs[i].first = heads[i].x;
-        runs[i].count = (i + 1 < n_heads ? heads[i + 1].x : n) - heads[i].x;
-        runs[i].world_view = heads[i].y >> 19;
-        runs[i].shader_mesh = heads[i].y & ((1u << 19) - 1u);
+    for (uint32_t i = 0; i < n_heads && i < cap; ++i) {          // class = world | view(5) | shader(8) | mesh(11)
+        runs[i].first = (uint32_t)heads[i].index;
+        runs[i].count = (uint32_t)((i + 1 < n_heads ? heads[i + 1].index : n) - heads[i].index);
+        runs[i].world_view = (uint32_t)(heads[i].cls >> 19);
+        runs[i].shader_mesh = (uint32_t)(heads[i].cls & ((1ull << 19) - 1ull));
     }
+    return ASTRE_OK;
+}
+
+int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path)
+{
+    if (!ctx || !path) return ASTRE_ERR_INVALID;
+    if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->last_stream));
+    *path = 0;
+    if (ctx->last_sorted) CK(cudaMemcpy(path, &ctx->d_sc->path, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return ASTRE_OK;
+}
+
+int astre_gpu_global_offsets_dev(astre_gpu_ctx *ctx, const uint32_t *all_counts_dev, uint32_t world_size, uint32_t rank,
+                                 uint32_t n_views, uint64_t *offsets_dev, uint64_t *view_totals_dev, void *stream)
+{
+    if (!ctx || !all_counts_dev || world_size == 0 || rank >= world_size) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "bad argument") : ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    k_global_offsets<<<1, 256, 0, s>>>(all_counts_dev, world_size, rank, n_views,
+                                       reinterpret_cast<unsigned long long *>(offsets_dev),
+                                       reinterpret_cast<unsigned long long *>(view_totals_dev));
+    CK_LAUNCH();
     return ASTRE_OK;
 }
 
@@ -1252,11 +1283,13 @@ int astre_gpu_publish_keys(astre_gpu_ctx *ctx, uint32_t parity, void *stream)
 {
     if (!ctx || parity > 1) return ASTRE_ERR_INVALID;
     if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    if (ctx->sort_pending || !(ctx->last_flags & ASTRE_FRAME_SORT))
+        return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_publish_keys needs a sorted frame (ASTRE_FRAME_SORT, or astre_gpu_sort after ASTRE_FRAME_SORT_LATER)");
     CK(cudaSetDevice(ctx->device));
     if (int rc = ensure_publish(ctx, parity)) return rc;
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     unsigned char *base = ctx->d_publish[parity];
-    k_publish_keys<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc->skip, ctx->last_sort_passes,
+    k_publish_keys<<<ctx->sm_count * 4, 256, 0, s>>>(ctx->d_keys[0], ctx->d_keys[1], &ctx->d_sc->result_buf, ctx->last_sorted ? 1u : 0u,
                                                      &ctx->d_ctl->key_total, ctx->max_keys,
                                                      reinterpret_cast<unsigned long long *>(base),
                                                      reinterpret_cast<unsigned long long *>(base + publish_layout(ctx->max_keys).samples_off),
@@ -1502,7 +1535,7 @@ int astre_gpu_merge_p2p(astre_gpu_ctx *ctx, uint32_t n_lists, uint32_t rank, con
     unsigned char *base = ctx->d_publish[parity];
     cfg.gridDim = dim3((unsigned)ctx->sm_count * 4u); cfg.blockDim = dim3(256);
     CK(cudaLaunchKernelEx(&cfg, k_publish_keys, (const unsigned long long *)ctx->d_keys[0], (const unsigned long long *)ctx->d_keys[1],
-                          (const uint32_t *)ctx->d_sc->skip, ctx->last_sort_passes, (const unsigned long long *)&ctx->d_ctl->key_total, cap,
+                          (const uint32_t *)&ctx->d_sc->result_buf, ctx->last_sorted ? 1u : 0u, (const unsigned long long *)&ctx->d_ctl->key_total, cap,
                           reinterpret_cast<unsigned long long *>(base), reinterpret_cast<unsigned long long *>(base + P.samples_off),
                           (const uint32_t *)ctx->d_counts, n_views, H.h[rank]));
     CK_LAUNCH();

@@ -27,7 +27,8 @@
 //    exact plane tests.  A view that keeps a large part of the tile (>= 40 of
 //    128) skips the queue and is tested four entities per lane instead;
 //  * compaction: keys are appended to a per-warp shared buffer (ballot + prefix
-//    popc) and flushed with one global reservation and coalesced 8-byte stores.
+//    popc) and flushed with one global reservation and coalesced 8-byte stores;
+//    the flush also counts every key into its bucket of the key sort (one RED).
 #pragma once
 #include "kernels_transform.cuh"
 
@@ -130,8 +131,7 @@ struct KeySink {
     unsigned long long *kbuf;     // shared, kKeyCap entries
     uint32_t fill;                // warp-uniform
     const FrameParams *P;
-    const SortPlan *plan;
-    uint32_t *s_hist;             // shared, this CTA's digit histograms [n_passes][256]
+    const BinPlan *bp;            // bucket digit of the key sort
     int lane;
 
     __device__ __forceinline__ void flush()
@@ -141,13 +141,12 @@ struct KeySink {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&P->ctl->key_total, (unsigned long long)fill);
             base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t n_passes = plan->n_passes;
+            const bool count_bins = bp->bits != 0;
             for (uint32_t i = lane; i < fill; i += 32) {
                 const unsigned long long k = kbuf[i], pos = base + i;
                 if (pos < P->key_cap) {
                     P->keys[pos] = k;
-                    for (uint32_t q = 0; q < n_passes; ++q)      // the sort's histograms, for free
-                        atomicAdd(&s_hist[q * 256 + sort_digit(plan->seg[q], k)], 1u);
+                    if (count_bins) atomicAdd(&P->bins[bin_digit(*bp, k)], 1u);   // the sort's bucket counts, for free (RED)
                 } else {
                     P->ctl->overflow = 1u;
                 }
@@ -251,7 +250,7 @@ __device__ __forceinline__ WorldBounds load_bounds(const float *sb, int idx)
 
 template <bool HIER, bool WORLDS, bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, 2)
-k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __grid_constant__ SortPlan plan,
+k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __grid_constant__ BinPlan bp,
               const __grid_constant__ LevelTable LT)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -260,7 +259,6 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     __shared__ __align__(8) unsigned long long s_bar[kWarpsPerBlock];
     __shared__ uint32_t s_counts[32];
     __shared__ uint32_t s_claim;                                  // next unclaimed warp tile of this CTA's list
-    __shared__ uint32_t s_hist[CULL ? kHistWords : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char *s_in = s_dyn + warp * kWarpSmemBytes;
@@ -281,7 +279,6 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
 
     if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_claim = kWarpsPerBlock;               // warp w starts with warp tile w
-    if (CULL) for (uint32_t i = threadIdx.x; i < plan.n_passes * 256u; i += kBlockThreads) s_hist[i] = 0;
     if (CULL && small_table) {
         for (uint32_t i = threadIdx.x; i < P.n_meshes * 2; i += kBlockThreads)   // 32-byte records, two float4 each
             reinterpret_cast<float4 *>(s_bounds)[i] = __ldg(reinterpret_cast<const float4 *>(P.bounds) + i);
@@ -297,7 +294,7 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     }
     __syncthreads();
 
-    KeySink sink{ kbuf, 0u, &P, &plan, s_hist, lane };
+    KeySink sink{ kbuf, 0u, &P, &bp, lane };
     uint32_t parity = 0;
 
     for (uint32_t level = 0; level < LT.n; ++level) {
@@ -532,11 +529,6 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
     __syncthreads();
     if (CULL && !WORLDS && threadIdx.x < F && s_counts[threadIdx.x])
         atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
-    if (CULL) {   // into one of the partial histograms (RED: several CTAs share a region)
-        uint32_t *region = P.block_hist + (size_t)(blockIdx.x % P.hist_regions) * kHistWords;
-        for (uint32_t i = threadIdx.x; i < plan.n_passes * 256u; i += kBlockThreads)
-            if (s_hist[i]) atomicAdd(&region[i], s_hist[i]);
-    }
 }
 
 }  // namespace astre

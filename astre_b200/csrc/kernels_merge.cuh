@@ -270,7 +270,9 @@ k_merge_tiles(const __grid_constant__ MergeLists L, const uint32_t *__restrict__
                 const uint32_t end = min(e + K, b1);
                 unsigned long long ka = i < na ? src[a0 + i] : ~0ull, kb = j < nb ? src[a1 + j] : ~0ull;
                 for (uint32_t k = 0; k < K; ++k, ++e) {                         // branch-free two-way merge
-                    const bool take = (ka >> ASTRE_KEY_SLOT_BITS) <= (kb >> ASTRE_KEY_SLOT_BITS);   // left run (lower ranks) first on equal class
+                    // left run (lower ranks) first on equal class; an exhausted run never wins (a real key may have
+                    // all class bits set, so the ~0 filler alone does not decide)
+                    const bool take = i < na && (!(j < nb) || (ka >> ASTRE_KEY_SLOT_BITS) <= (kb >> ASTRE_KEY_SLOT_BITS));
                     const uint32_t idx = take ? a0 + i : a1 + j;
                     if (e < end) { dst[e] = take ? ka : kb; dtag[e] = stag[idx]; }
                     i += take ? 1u : 0u; j += take ? 0u : 1u;
@@ -362,14 +364,13 @@ __global__ void k_peer_sync(const PeerHeaders H, const uint32_t sig, const uint3
 // no host round trip.
 __global__ void __launch_bounds__(256)
 k_publish_keys(const unsigned long long *__restrict__ buf0, const unsigned long long *__restrict__ buf1,
-               const uint32_t *__restrict__ skip, uint32_t n_passes, const unsigned long long *__restrict__ key_total,
+               const uint32_t *__restrict__ result_buf, uint32_t sorted, const unsigned long long *__restrict__ key_total,
                unsigned long long cap, unsigned long long *__restrict__ dst, unsigned long long *__restrict__ samples,
                const uint32_t *__restrict__ counts, uint32_t n_views, PublishHeader *__restrict__ header)
 {
     cudaGridDependencySynchronize();
     if (header && blockIdx.x == 0 && threadIdx.x < n_views) header->counts[threadIdx.x] = counts[threadIdx.x];
-    uint32_t which = 0;
-    for (uint32_t p = 0; p < n_passes; ++p) which ^= skip[p] ? 0u : 1u;
+    const uint32_t which = sorted ? *result_buf : 0u;   // the key buffer the sort ended in (decided on the device)
     const unsigned long long *src = which ? buf1 : buf0;
     const unsigned long long n = min(*key_total, cap);
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;

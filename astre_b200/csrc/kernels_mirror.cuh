@@ -109,8 +109,12 @@ k_interpolate(const float *__restrict__ tiles_a, const float *__restrict__ tiles
             if (c > 1.0f - 1.1920928955078125e-7f) {
                 q[3] = mixf(aw, zw, alpha); q[0] = mixf(ax, zx, alpha); q[1] = mixf(ay, zy, alpha); q[2] = mixf(az, zz, alpha);
             } else {
-                const float ang = acosf(c);
-                const float s0 = sinf(fmul(fsub(1.0f, alpha), ang)), s1 = sinf(fmul(alpha, ang)), sd = sinf(ang);
+                // acos / sin evaluated in double and rounded once: the correctly rounded float in all but ~1e-8 of
+                // the cases, i.e. at most 1 ULP from any libm's acosf / sinf (the reference's results depend on
+                // the platform's libm here, glm::slerp calls std::acos / std::sin)
+                const float ang = (float)acos((double)c);
+                const float s0 = (float)sin((double)fmul(fsub(1.0f, alpha), ang)), s1 = (float)sin((double)fmul(alpha, ang)),
+                            sd = (float)sin((double)ang);
                 q[3] = __fdiv_rn(fadd(fmul(s0, aw), fmul(s1, zw)), sd);
                 q[0] = __fdiv_rn(fadd(fmul(s0, ax), fmul(s1, zx)), sd);
                 q[1] = __fdiv_rn(fadd(fmul(s0, ay), fmul(s1, zy)), sd);
@@ -131,17 +135,126 @@ k_interpolate(const float *__restrict__ tiles_a, const float *__restrict__ tiles
     }
 }
 
-// f2: heads of the draw runs of the sorted list: key i starts a run when its class
-// (key >> class_shift = world|view|shader|mesh) differs from key i-1's.  Unordered emission.
-__global__ void k_run_heads(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t class_shift,
-                            uint2 *__restrict__ heads, uint32_t cap, uint32_t *__restrict__ counter)
+// f2: heads of the draw runs of the sorted list, in list order.  Key i starts a run when its class
+// (key >> class_shift = world | view | shader | mesh, up to 44 bits: carried as 64) differs from key i-1's.
+// Three small launches: heads per CTA (each CTA owns a contiguous piece of the list), scan of those counts,
+// ordered write -- no host-side sort.
+struct RunHead { unsigned long long index, cls; };
+constexpr int kRunThreads = 256;
+
+__device__ __forceinline__ bool run_head_at(const unsigned long long *__restrict__ keys, uint32_t i, uint32_t class_shift)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t cls = (uint32_t)(keys[i] >> class_shift);
-        if (i == 0 || cls != (uint32_t)(keys[i - 1] >> class_shift)) {
-            const uint32_t at = atomicAdd(counter, 1u);
-            if (at < cap) heads[at] = make_uint2(i, cls);
+    return i == 0 || (keys[i] >> class_shift) != (keys[i - 1] >> class_shift);
+}
+
+__global__ void __launch_bounds__(kRunThreads)
+k_run_count(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t class_shift, uint32_t per_cta,
+            uint32_t *__restrict__ cta_counts)
+{
+    __shared__ uint32_t s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const uint32_t lo = blockIdx.x * per_cta, hi = min(lo + per_cta, n);
+    uint32_t c = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kRunThreads) c += run_head_at(keys, i, class_shift) ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_total, c);
+    __syncthreads();
+    if (threadIdx.x == 0) cta_counts[blockIdx.x] = s_total;
+}
+
+// exclusive scan of cta_counts[0..n_ctas) in place; cta_counts[n_ctas] = total.  One block.
+__global__ void __launch_bounds__(1024)
+k_run_scan(uint32_t *__restrict__ cta_counts, uint32_t n_ctas)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_ctas; base += 1024u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t c = i < n_ctas ? cta_counts[i] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t off = s_carry;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (i < n_ctas) cta_counts[i] = off + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = off + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cta_counts[n_ctas] = s_carry;
+}
+
+__global__ void __launch_bounds__(kRunThreads)
+k_run_write(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t class_shift, uint32_t per_cta,
+            const uint32_t *__restrict__ cta_offsets, RunHead *__restrict__ heads, uint32_t cap)
+{
+    __shared__ uint32_t s_warp[kRunThreads / 32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lo = blockIdx.x * per_cta, hi = min(lo + per_cta, n);
+    if (threadIdx.x == 0) s_base = cta_offsets[blockIdx.x];
+    __syncthreads();
+    for (uint32_t base = lo; base < hi; base += kRunThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const bool head = i < hi && run_head_at(keys, i, class_shift);
+        const uint32_t bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = s_base, total = 0;
+#pragma unroll
+        for (int w = 0; w < kRunThreads / 32; ++w) { if (w < warp) off += s_warp[w]; total += s_warp[w]; }
+        if (head) {
+            const uint32_t at = off + __popc(bal & ((1u << lane) - 1u));
+            if (at < cap) { heads[at].index = i; heads[at].cls = keys[i] >> class_shift; }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+}
+
+// 8e: this rank's segment offsets in the global per-view draw lists, on the device.  all_counts is the
+// all-gathered table [world_size][n_views]; the global list is ordered (view, rank, key), so
+// offsets[v] = sum of every view before v over all ranks + sum of view v over the ranks before this one.
+// One block (the table is tiny: n_views <= worlds x views of one shard).
+__global__ void __launch_bounds__(256)
+k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, uint32_t rank, uint32_t n_views,
+                 unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
+{
+    __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_views; base += 256u) {
+        const uint32_t v = base + threadIdx.x;
+        unsigned long long total = 0, before = 0;
+        if (v < n_views)
+            for (uint32_t r = 0; r < world_size; ++r) {
+                const unsigned long long c = all_counts[(size_t)r * n_views + v];
+                if (r < rank) before += c;
+                total += c;
+            }
+        unsigned long long incl = total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_carry;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (v < n_views) {
+            if (offsets) offsets[v] = off + incl - total + before;
+            if (view_totals) view_totals[v] = total;
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = off + incl;
+        __syncthreads();
     }
 }
 

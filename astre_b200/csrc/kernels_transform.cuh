@@ -79,8 +79,7 @@ struct FrameParams {
     unsigned long long *keys;
     uint32_t *counts;              // [n_worlds*views_per_world]
     FrameControl *ctl;
-    uint32_t *block_hist;          // [hist_regions][8][256] partial digit histograms for the sort
-    uint32_t hist_regions;         // CTA b adds into region b % hist_regions
+    uint32_t *bins;                // bucket counts of the key sort (kernels_sort.cuh): one RED per emitted key
     uint32_t claim_groups;         // work counters of a flat frame (0: none); CTA b draws from group b % claim_groups
     unsigned long long key_cap;
     uint32_t n_meshes;
@@ -168,7 +167,23 @@ __device__ __forceinline__ unsigned long long make_key(uint32_t wbits, uint32_t 
     return k;
 }
 
-// Digit plan of the key sort (kernels_sort.cuh); the cull kernels histogram the digits as they emit keys.
+// Bucket digit of the key sort (kernels_sort.cuh): the top `bits` key bits that can differ, packed in key
+// order.  The cull kernels count every key they emit into bins[bin_digit(key)]; bits == 0: no sort wanted.
+constexpr int kBinSegs = 8;
+struct BinPlan {
+    uint32_t n_segs, bits;
+    uint32_t shift[kBinSegs], mask[kBinSegs], lshift[kBinSegs];   // digit = OR of ((key >> shift) & mask) << lshift
+};
+__host__ __device__ __forceinline__ uint32_t bin_digit(const BinPlan &bp, unsigned long long key)
+{
+    uint32_t d = 0;
+#pragma unroll
+    for (int s = 0; s < kBinSegs; ++s)
+        if ((uint32_t)s < bp.n_segs) d |= ((uint32_t)(key >> bp.shift[s]) & bp.mask[s]) << bp.lshift[s];
+    return d;
+}
+
+// Digit plan of the LSD fallback of the key sort (kernels_sort.cuh).
 constexpr int kSortPasses = 8;
 constexpr int kSortSegs = 4;
 constexpr int kHistWords = kSortPasses * 256;
@@ -279,7 +294,7 @@ __device__ __forceinline__ void cull_views(const Views &V, const uint32_t F, con
 // Writes the keys of one lane starting at `pos`; with s_counts != nullptr also
 // bumps the per-view shared counters (one world, sparse case).
 template <int K, class Views>
-__device__ __forceinline__ void emit_keys(const FrameParams &P, const SortPlan &plan, const Views &V, uint32_t world,
+__device__ __forceinline__ void emit_keys(const FrameParams &P, const BinPlan &bp, const Views &V, uint32_t world,
                                           const WorldBounds (&wb)[K], const uint32_t (&vis)[K],
                                           const uint32_t (&meta)[K], const uint32_t (&local)[K],
                                           unsigned long long pos, uint32_t *s_counts)
@@ -294,8 +309,7 @@ __device__ __forceinline__ void emit_keys(const FrameParams &P, const SortPlan &
                                                     depth14(wb[k], V.depth(v), V.depth_scale(v)), local[k]);
             if (pos < P.key_cap) {
                 P.keys[pos] = key;
-                for (uint32_t q = 0; q < plan.n_passes; ++q)      // region 0; launches of one frame are stream-ordered
-                    atomicAdd(&P.block_hist[q * 256 + sort_digit(plan.seg[q], key)], 1u);
+                if (bp.bits) atomicAdd(&P.bins[bin_digit(bp, key)], 1u);
             } else {
                 P.ctl->overflow = 1u;
             }
@@ -338,7 +352,7 @@ __device__ __forceinline__ void add_counts(const FrameParams &P, uint32_t world,
 // per lane, staged stores, task queue) needs ~18 us for its first tile.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlockThreads)
-k_transform_cull_indexed(const FrameParams P, const __grid_constant__ SortPlan plan, const uint32_t *__restrict__ slots,
+k_transform_cull_indexed(const FrameParams P, const __grid_constant__ BinPlan bp, const uint32_t *__restrict__ slots,
                          const uint32_t first, const uint32_t n)
 {
     __shared__ float4 s_scratch[kBlockThreads * 4];
@@ -391,7 +405,7 @@ k_transform_cull_indexed(const FrameParams P, const __grid_constant__ SortPlan p
             base = __shfl_sync(0xffffffffu, base, 0);
             for (uint32_t v = 0; v < P.views_per_world; ++v)
                 if ((vis[0] >> v) & 1u) atomicAdd(&P.counts[(size_t)world * P.views_per_world + v], 1u);
-            if (cnt) emit_keys<1>(P, plan, V, world, wb, vis, meta, local, base + (incl - cnt), nullptr);
+            if (cnt) emit_keys<1>(P, bp, V, world, wb, vis, meta, local, base + (incl - cnt), nullptr);
         }
     }
 }

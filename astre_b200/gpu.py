@@ -130,6 +130,17 @@ class GpuContext:
         """Sort the keys of a frame that ran with FRAME_CULL | FRAME_SORT_LATER (lets the count exchange overlap the sort)."""
         self._check(self._lib.astre_gpu_sort(self._h, stream))
 
+    def last_sort_path(self):
+        """0 = no sort ran, 1 = bucket sort, 2 = LSD radix fallback (decided on the device)."""
+        v = C.c_uint32(0)
+        self._check(self._lib.astre_gpu_last_sort_path(self._h, C.byref(v)))
+        return int(v.value)
+
+    def global_offsets_dev(self, all_counts_ptr, world_size, rank, n_views, offsets_ptr, totals_ptr=0, stream=None):
+        """Segment offsets of this rank from an all-gathered count table, all in device memory (stream-ordered)."""
+        self._check(self._lib.astre_gpu_global_offsets_dev(self._h, int(all_counts_ptr), int(world_size), int(rank), int(n_views),
+                                                           int(offsets_ptr) or None, int(totals_ptr) or None, stream))
+
     def sync(self):
         self._check(self._lib.astre_gpu_sync(self._h))
 

@@ -10,11 +10,13 @@ Mesh ids 0..7 stand for the reference's prefab meshes (cube, quad, cone,
 cylinder, icosphere1-3, dome -- engine/modules/Render/src/vertex.cpp); their
 local bounds are +-0.5 boxes and unit spheres.
 """
+import ctypes as _C
+import os as _os
 from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import gpu as _gpu
+from . import gpu as _gpu     # constants and (lazily) the product's host-side view builders; importing it loads nothing
 
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
@@ -117,8 +119,37 @@ class Scene:
                      n_worlds, self.entities_per_world)
 
 
+_SCENEGEN = None
+
+
+def _scenegen():
+    """tools/_build/libscenegen.so (tools/scenegen/scenegen.c): the same generator in C with OpenMP -- 64M entities
+    in about a second instead of a minute.  Harness only; absent or ASTRE_SCENEGEN=numpy -> the numpy definition below."""
+    global _SCENEGEN
+    if _SCENEGEN is None:
+        _SCENEGEN = False
+        so = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tools", "_build", "libscenegen.so")
+        if _os.environ.get("ASTRE_SCENEGEN", "") != "numpy" and _os.path.exists(so):
+            lib = _C.CDLL(so)
+            lib.scenegen_block.restype = None
+            lib.scenegen_block.argtypes = [_C.c_uint64, _C.c_uint64, _C.c_uint64, _C.c_float, _C.c_float, _C.c_float, _C.c_float,
+                                           _C.c_uint32, _C.c_uint32, _C.c_uint8] + [_C.c_void_p] * 6
+            _SCENEGEN = lib
+    return _SCENEGEN
+
+
 def entity_block(seed, lo, hi, pos_range, scale_range, n_mesh=8, n_shader=4):
     """TRS + visual attributes of entity indices [lo, hi) of the stream `seed`."""
+    lib = _scenegen()
+    if lib:
+        n = int(hi) - int(lo)
+        pos, rot, scale = np.empty((n, 3), np.float32), np.empty((n, 4), np.float32), np.empty((n, 3), np.float32)
+        mesh, shader, flags = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.uint8)
+        lib.scenegen_block(int(seed), int(lo), int(hi), np.float32(-pos_range), np.float32(pos_range - -pos_range),
+                           np.float32(scale_range[0]), np.float32(scale_range[1] - scale_range[0]), n_mesh, n_shader,
+                           _gpu.PHASE_OPAQUE | _gpu.PHASE_SHADOW_CASTER,
+                           *[a.ctypes.data for a in (pos, rot, scale, mesh, shader, flags)])
+        return pos, rot, scale, mesh, shader, flags
     idx = np.arange(lo, hi, dtype=np.uint64)
     pos = np.stack([_uniform(seed, idx, c, -pos_range, pos_range) for c in range(3)], axis=1)
     q = np.stack([_uniform(seed, idx, 3 + c, -1.0, 1.0) for c in range(4)], axis=1)
@@ -144,12 +175,35 @@ CAMERA = dict(pos=(0.0, 5.0, 15.0), forward=(0.0, 0.0, -1.0), up=(0.0, 1.0, 0.0)
               fov_deg=60.0, aspect=1.7, z_near=0.1, z_far=1000.0)   # level_0.json:120-141
 
 
+class _ProductMatrices:
+    """View builders of the product library (host-only C++, astre_camera_matrices / astre_ortho_view_matrix)."""
+
+    @staticmethod
+    def camera_clip(pos, fwd, up, fov_deg, aspect, z_near, z_far):
+        return _gpu.camera_matrices(pos, fwd, up, fov_deg, aspect, z_near, z_far)[2]
+
+    @staticmethod
+    def ortho_view(eye, center, up, l, r, b, t, n, f):
+        return _gpu.ortho_view_matrix(eye, center, up, l, r, b, t, n, f)
+
+
+_MATRICES = _ProductMatrices
+
+
+def set_matrix_provider(provider):
+    """Who builds the clip matrices of the synthetic views.  Default: the product's host math.  bench.py's
+    reference arm installs an oracle-backed provider so that its process never maps the product library
+    (both produce identical bits: tests/test_host_math.py)."""
+    global _MATRICES
+    _MATRICES = provider or _ProductMatrices
+
+
 def camera_clip(yaw_deg=0.0):
     """Clip matrix of the level_0 camera, optionally yawed about +Y."""
     a = np.float32(np.deg2rad(np.float32(yaw_deg)))
     fwd = (float(-np.sin(a)), 0.0, float(-np.cos(a)))
-    return _gpu.camera_matrices(CAMERA["pos"], fwd, CAMERA["up"], CAMERA["fov_deg"], CAMERA["aspect"],
-                                CAMERA["z_near"], CAMERA["z_far"])[2]
+    return _MATRICES.camera_clip(CAMERA["pos"], fwd, CAMERA["up"], CAMERA["fov_deg"], CAMERA["aspect"],
+                                 CAMERA["z_near"], CAMERA["z_far"])
 
 
 def cascade_clips(splits=(10.0, 40.0, 160.0, 1000.0)):
@@ -167,8 +221,8 @@ def cascade_clips(splits=(10.0, 40.0, 160.0, 1000.0)):
         half = (far - near) * np.float32(0.75)
         dist = half + np.float32(50.0)
         eye = centre - direction * dist
-        clips.append(_gpu.ortho_view_matrix(eye, centre, (0.0, 1.0, 0.0), -half, half, -half, half,
-                                            0.1, float(dist + half)))
+        clips.append(_MATRICES.ortho_view(eye, centre, (0.0, 1.0, 0.0), -half, half, -half, half,
+                                          0.1, float(dist + half)))
         near = far
     return clips
 

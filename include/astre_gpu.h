@@ -69,9 +69,9 @@ enum {
 enum {
     ASTRE_FRAME_TRANSFORM = 1u << 0,  /* TransformSystem::run matrices (always implied)     */
     ASTRE_FRAME_CULL      = 1u << 1,  /* frustum test + compaction + key emission            */
-    ASTRE_FRAME_SORT      = 1u << 2,  /* device radix sort of the emitted keys               */
+    ASTRE_FRAME_SORT      = 1u << 2,  /* device sort of the emitted keys                     */
     ASTRE_FRAME_BASIS     = 1u << 3,  /* forward/up/right of every entity                    */
-    ASTRE_FRAME_SORT_LATER = 1u << 4, /* prepare the sort (digit histograms) but run it in astre_gpu_sort */
+    ASTRE_FRAME_SORT_LATER = 1u << 4, /* prepare the sort (bucket counts) but run it in astre_gpu_sort */
     ASTRE_FRAME_ALL       = 7u
 };
 
@@ -168,6 +168,11 @@ ASTRE_API int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *st
  * needs the per-view counts -- the multi-GPU count exchange -- while
  * the sort runs.  Afterwards the frame reads exactly like one run with ASTRE_FRAME_SORT. */
 ASTRE_API int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream);
+/* Which way the last frame's keys were sorted (decided on the device from the bucket sizes):
+ * 0 = no sort ran, 1 = bucket sort, 2 = LSD radix fallback.  Spec-defined stage (SURVEY.md
+ * Appendix B): the reference has no draw-order sort (deferred_shading.cpp:115,151 walk a hash map).
+ * Synchronises. */
+ASTRE_API int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path);
 ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
 /* Makes every later call on ctx (mirror updates, frames with stream == NULL,
  * read-backs) enqueue on the caller's cudaStream_t instead of the context's own
@@ -334,6 +339,12 @@ ASTRE_API void astre_ortho_view_matrix(const float *eye3, const float *center3, 
  * all_counts is [world_size][n_views]; offsets/view_totals are [n_views]. */
 ASTRE_API void astre_global_offsets(const uint32_t *all_counts, uint32_t world_size, uint32_t rank,
                                     uint32_t n_views, uint64_t *offsets, uint64_t *view_totals);
+/* The same on the device and stream-ordered, for an all-gathered count table that never leaves the GPU
+ * (all pointers are device pointers; offsets_dev / view_totals_dev may be NULL): the per-frame exchange of
+ * SURVEY.md 8e then needs no host round trip.  stream: cudaStream_t cast to void* (NULL = the context's). */
+ASTRE_API int astre_gpu_global_offsets_dev(astre_gpu_ctx *ctx, const uint32_t *all_counts_dev, uint32_t world_size,
+                                           uint32_t rank, uint32_t n_views, uint64_t *offsets_dev,
+                                           uint64_t *view_totals_dev, void *stream);
 
 #ifdef __cplusplus
 }

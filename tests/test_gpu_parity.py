@@ -316,32 +316,67 @@ def test_stress_moving_camera_and_dirty_sets(oracle):
                 assert np.all(keys[1:] > keys[:-1]) and counts.sum() == len(keys)
 
 
-@pytest.mark.parametrize("ties", ["0", "1"])
-def test_sort_ties_long_runs(oracle, ties, monkeypatch):
-    """ASTRE_SORT_TIES=1 (optional sort mode) and the default full sort on a scene made of ties.  Keys that agree on everything above the slot field (same view, shader, mesh and depth bucket) are ordered
-    by the tie fix-up: short runs by one thread, runs longer than 32 by one CTA each.  Entities stacked at a few
-    positions make runs of every length, including one of 40k keys."""
-    if ties == "1":
-        monkeypatch.setenv("ASTRE_SORT_TIES", "1")
-    else:
-        monkeypatch.delenv("ASTRE_SORT_TIES", raising=False)
-    n = 100_000
+def _stacked_scene(n=100_000):
+    """Entities stacked at a few positions: keys that agree on view, shader, mesh AND depth -- the bucket sort's
+    worst case (one bucket of ~37k keys), runs of every length, plus a spread-out tail."""
     s = scenes.config1(n)
     rng = np.random.default_rng(17)
     spots = np.array([[0, 5, -20], [3, 5, -40], [-6, 4, -80], [10, 8, -200]], np.float32)
     group = np.zeros(n, np.int64)
     group[40_000:70_000] = 1
-    group[70_000:70_040] = 2            # 40 keys per (shader, mesh) class -> short and barely-long runs
+    group[70_000:70_040] = 2            # 40 keys per (shader, mesh) class
     group[70_040:] = 3
     s.pos = spots[group].copy()
-    s.pos[90_000:] += rng.normal(scale=30.0, size=(n - 90_000, 3)).astype(np.float32)   # a spread-out tail
+    s.pos[90_000:] += rng.normal(scale=30.0, size=(n - 90_000, 3)).astype(np.float32)
     s.rot[:] = np.array([0, 0, 0, 1], np.float32)
     s.scale[:] = 1.0
     s.mesh[:40_000] = 0                 # one class: a single run of ~37k keys (every 16th is invisible)
     s.shader[:40_000] = 0
     s.flags = gpu.make_flags(np.arange(n) % 16 != 15, np.full(n, 5, np.uint8))
-    n_keys = check_scene(oracle, s)
-    assert n_keys > 80_000
+    return s
+
+
+SORT_MODES = {"auto": {}, "force_lsd": {"ASTRE_SORT_FORCE_LSD": "1"}, "bins8": {"ASTRE_SORT_BIN_BITS": "8"},
+              "bins12": {"ASTRE_SORT_BIN_BITS": "12"}, "bins22": {"ASTRE_SORT_BIN_BITS": "22"}}
+
+
+@pytest.mark.parametrize("mode", list(SORT_MODES))
+def test_sort_paths(oracle, mode, monkeypatch):
+    """The key sort: bucket sort (any bucket-digit width sorts correctly) and the LSD fallback, which the device
+    picks by itself when buckets are crowded.  Same list bit for bit on every path."""
+    for k in ("ASTRE_SORT_FORCE_LSD", "ASTRE_SORT_BIN_BITS"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in SORT_MODES[mode].items():
+        monkeypatch.setenv(k, v)
+    for scene in (scenes.config3(300_000), scenes.config5(n_worlds=24, entities_per_world=4096), _stacked_scene()):
+        o_world, o_keys, o_counts = oracle.frame(scene)
+        with GpuContext(scene.n, max_views=scene.views_per_world) as ctx:
+            scenes.load_into(ctx, scene)
+            for _ in range(3):           # frame 2 and 3 size their buckets from the previous frame's key count
+                ctx.frame()
+                keys, path = ctx.read_all_keys(), ctx.last_sort_path()
+                assert np.array_equal(keys, o_keys), (mode, scene.name, path)
+                assert np.array_equal(ctx.read_counts(), o_counts)
+                if mode == "force_lsd" or scene.name == "config1-flat-10k":     # the stacked scene keeps config1's name
+                    assert path == 2, (mode, scene.name, path)                   # crowded buckets: the fallback, chosen on the device
+                elif mode in ("auto", "bins22"):
+                    assert path == 1, (mode, scene.name, path)
+
+
+def test_sort_bucket_count_follows_the_key_count(oracle):
+    """One context, frames with very different key counts (the bucket count is a hint from the last frame)."""
+    s = scenes.config1(200_000)
+    with GpuContext(s.n, max_views=2) as ctx:
+        scenes.load_into(ctx, s)
+        dense = s.pos * np.float32(0.02)
+        dense[:, 2] -= np.float32(40.0)
+        for pos in (s.pos, dense.astype(np.float32), s.pos, dense.astype(np.float32)):
+            s.pos = np.ascontiguousarray(pos, np.float32)
+            ctx.update_trs_range(0, s.n, s.pos, s.rot, s.scale)
+            _, o_keys, o_counts = oracle.frame(s)
+            for _ in range(2):
+                ctx.frame()
+                assert np.array_equal(ctx.read_all_keys(), o_keys) and np.array_equal(ctx.read_counts(), o_counts)
 
 
 def test_deferred_sort_equals_one_call(oracle):

@@ -195,31 +195,6 @@ def test_view_box_contains_the_view_volume(oracle):
     assert 980 < hi[0] < 983 and -983 < lo[0] < -980 and -986 < lo[2] < -984 and 14.9 < hi[2] < 15.1
 
 
-def test_reference_layout_baseline_matches_oracle(oracle):
-    """B0 (oracle/ref_store.cpp): the oracle arithmetic over a hash map of per-entity structs gives the same matrices."""
-    import ctypes as C
-    import subprocess
-    so = os.path.join(oracle_lib.ORACLE_DIR, "_build", "libastre_refstore.so")
-    subprocess.run(["make", "-C", oracle_lib.ORACLE_DIR], check=True, capture_output=True)
-    lib = C.CDLL(so)
-    lib.refstore_create.restype = C.c_void_p
-    lib.refstore_visual.restype = C.c_uint64
-    s = scenes.config1(5000)
-    p = oracle_lib._p
-    st = lib.refstore_create(C.c_uint32(s.n), p(s.pos, C.c_float), p(s.rot, C.c_float), p(s.scale, C.c_float),
-                             p(s.mesh, C.c_uint32), p(s.shader, C.c_uint32), p(s.flags, C.c_uint8))
-    try:
-        lib.refstore_transform(C.c_void_p(st))
-        assert lib.refstore_visual(C.c_void_p(st)) == s.n
-        ref = oracle.transform_flat(s.pos, s.rot, s.scale)
-        m = np.empty(16, np.float32)
-        for i in (0, 1, 63, 1023, 4999):
-            lib.refstore_read_world(C.c_void_p(st), C.c_uint32(i), p(m, C.c_float))
-            assert np.array_equal(oracle_lib.bits(m), oracle_lib.bits(ref[i]))
-    finally:
-        lib.refstore_destroy(C.c_void_p(st))
-
-
 def test_trs_matrix_conventions_against_scipy(oracle):
     """Tolerance-level check of the conventions (not of the bits): quaternion order x,y,z,w, right-handed active
     rotation, column-major storage, M = T * R * S -- against scipy's independent Rotation class."""

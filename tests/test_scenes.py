@@ -37,3 +37,17 @@ def test_config5_world_shards():
     half = s.shard(1, 2)
     assert half.n_worlds == 4 and np.array_equal(half.pos, s.pos[4 * 256:])
     assert np.array_equal(half.clip, s.clip[4:])
+
+
+def test_c_generator_matches_the_numpy_definition(monkeypatch):
+    """tools/scenegen (harness speed-up) and the numpy definition produce the same bits."""
+    if not scenes._scenegen():
+        import pytest
+        pytest.skip("tools/_build/libscenegen.so not built")
+    fast = [scenes.entity_block(7, 1000, 9000, 200.0, (0.25, 4.0)), scenes.entity_block(2, 0, 3000, 10.0, (0.8, 1.25), 5, 3)]
+    monkeypatch.setattr(scenes, "_SCENEGEN", False)
+    slow = [scenes.entity_block(7, 1000, 9000, 200.0, (0.25, 4.0)), scenes.entity_block(2, 0, 3000, 10.0, (0.8, 1.25), 5, 3)]
+    for f, s in zip(fast, slow):
+        for a, b in zip(f, s):
+            assert a.dtype == b.dtype and a.shape == b.shape
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
