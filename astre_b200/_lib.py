@@ -47,7 +47,7 @@ SIGNATURES = {
     "astre_gpu_frame": (C.c_int, [_P, C.c_uint32, _P]),
     "astre_gpu_sort": (C.c_int, [_P, _P]),
     "astre_gpu_last_sort_path": (C.c_int, [_P, _U32]),
-    "astre_gpu_global_offsets_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "astre_gpu_global_offsets_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "astre_gpu_sync": (C.c_int, [_P]),
     "astre_gpu_set_stream": (C.c_int, [_P, _P]),
     "astre_gpu_launch_count": (C.c_uint64, [_P]),
@@ -88,6 +88,7 @@ SIGNATURES = {
     "astre_light_space_matrix": (C.c_int, [_F, _F, C.c_int, C.c_float, _F]),
     "astre_ortho_view_matrix": (None, [_F, _F, _F, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _F]),
     "astre_global_offsets": (None, [_U32, C.c_uint32, C.c_uint32, C.c_uint32, _U64, _U64]),
+    "astre_global_offsets_rank_major": (None, [_U32, C.c_uint32, C.c_uint32, C.c_uint32, _U64, _U64]),
 }
 
 

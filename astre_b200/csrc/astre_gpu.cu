@@ -702,7 +702,7 @@ int astre_gpu_set_views(astre_gpu_ctx *ctx, uint32_t n_views, const float *clip1
 // The sort of the frame's keys: bin scan -> scatter -> rank, then the LSD fallback, which returns at once unless
 // the scan found the buckets too crowded (all decided on the device).  Programmatic dependent launch: each kernel of
 // the chain is made resident while its predecessor drains and blocks in cudaGridDependencySynchronize().
-static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &plan, cudaStream_t s)
+static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &plan, uint32_t n_counts, cudaStream_t s)
 {
     if (!bp.bits) return ASTRE_OK;                 // no key bit can differ: at most one key
     cudaLaunchAttribute pdl;
@@ -713,7 +713,7 @@ static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &pl
     const unsigned long long cap = ctx->max_keys;
     const uint32_t n_bins = 1u << bp.bits;
     const FrameControl *ctl = ctx->d_ctl;
-    const uint32_t wide = (uint32_t)ctx->sm_count * 4u;
+    const uint32_t wide = (uint32_t)ctx->sm_count * 8u;
     cfg.gridDim = dim3(std::max(n_bins / kScanTile, 1u)); cfg.blockDim = dim3(1024);
     CK(cudaLaunchKernelEx(&cfg, k_bin_scan, ctx->d_bins, n_bins, ctx->d_sc, ctx->d_chunk_first));
     CK_LAUNCH();
@@ -722,11 +722,11 @@ static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &pl
                           (const SortControl *)ctx->d_sc, ctl, cap, ctx->force_lsd));
     CK_LAUNCH();
     CK(cudaLaunchKernelEx(&cfg, k_bin_rank, (const unsigned long long *)ctx->d_keys[1], ctx->d_keys[0], (const uint32_t *)ctx->d_bins,
-                          (const uint32_t *)ctx->d_chunk_first, bp, ctx->d_sc, ctl, cap, ctx->force_lsd));
+                          (const uint32_t *)ctx->d_chunk_first, bp, ctx->d_sc, ctl, cap, ctx->force_lsd, ctx->d_hint));
     CK_LAUNCH();
     cfg.gridDim = dim3((unsigned)ctx->sort_grid); cfg.blockDim = dim3(kSortThreads);
     CK(cudaLaunchKernelEx(&cfg, k_sort_lsd_all, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, ctl, cap,
-                          ctx->force_lsd));
+                          ctx->force_lsd, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts, ctx->d_hint));
     CK_LAUNCH();
     return ASTRE_OK;
 }
@@ -768,13 +768,13 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         live |= ((1ull << bits_for(ctx->views_per_world ? ctx->views_per_world - 1 : 0)) - 1ull) << (59 - wb);
         if (wb) live |= ((1ull << wb) - 1ull) << (64 - wb);
         plan = make_sort_plan(live);
-        // buckets of ~4-8 keys: one bin per 4 keys of the last frame that finished (a hint -- any width sorts correctly;
+        // buckets of ~4-8 keys: one bin per 8 keys of the last frame that finished (a hint -- any width sorts correctly;
         // before the first frame: one key per 16 entity-view pairs)
         const unsigned long long seen = *(volatile unsigned long long *)ctx->h_hint;
         const unsigned long long expect = seen != ~0ull ? std::min<unsigned long long>(seen, ctx->max_keys)
                                                         : (unsigned long long)n * ctx->views_per_world / 16ull;
         uint32_t want = kMinBinBits;
-        while (want < ctx->cap_bin_bits && (1ull << want) * 4ull < expect) ++want;
+        while (want < ctx->cap_bin_bits && (1ull << want) * 8ull < expect) ++want;
         if (ctx->bin_bits_override >= 0) want = std::min<uint32_t>((uint32_t)ctx->bin_bits_override, ctx->cap_bin_bits);
         bp = make_bin_plan(live, want);
     }
@@ -804,8 +804,17 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             else if (hier) fn = worlds ? (const void *)k_frame_fused<true, true, true> : (const void *)k_frame_fused<true, false, true>;
             else fn = worlds ? (const void *)k_frame_fused<false, true, true> : (const void *)k_frame_fused<false, false, true>;
             void *args[] = { (void *)&P, (void *)&ctx->h_viewset, (void *)&bp, (void *)&LT };
-            if (LT.n > 1) launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
-            else launch_err = cudaLaunchKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
+            if (LT.n > 1) {
+                launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
+            } else {
+                cudaLaunchAttribute pdl;
+                pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(g); cfg.blockDim = dim3(kBlockThreads); cfg.dynamicSmemBytes = kFusedSmemBytes;
+                cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+                launch_err = cudaLaunchKernelExC(&cfg, fn, args);
+            }
             barrier_rounds += (LT.n - 1) * g;
             claim_sets += LT.n * std::min<uint32_t>(ctx->claim_groups, g);
         };
@@ -858,12 +867,13 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         }
     }
 
-    if (sort_now) { if (int rc = launch_sort(ctx, bp, plan, s)) return rc; }
+    const bool counts_in_sort = sort_now && bp.bits != 0;      // the sort's last launch also scans the counts
+    if (sort_now) { if (int rc = launch_sort(ctx, bp, plan, n_counts, s)) return rc; }
     ctx->sort_pending = sort && !sort_now;
     ctx->pending_plan = plan;
     ctx->pending_bins = bp;
     ctx->last_sorted = sort_now && bp.bits != 0;
-    if (n_counts) {
+    if (n_counts && !counts_in_sort) {
         cudaLaunchAttribute pdl;
         pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
         pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
@@ -888,7 +898,7 @@ int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream)
         return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_sort needs a frame run with ASTRE_FRAME_CULL | ASTRE_FRAME_SORT_LATER");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (int rc = launch_sort(ctx, ctx->pending_bins, ctx->pending_plan, s)) return rc;
+    if (int rc = launch_sort(ctx, ctx->pending_bins, ctx->pending_plan, 0u, s)) return rc;
     ctx->last_sorted = ctx->pending_bins.bits != 0;
     ctx->last_flags = (ctx->last_flags & ~(uint32_t)ASTRE_FRAME_SORT_LATER) | ASTRE_FRAME_SORT;
     ctx->sort_pending = false;
@@ -1017,12 +1027,13 @@ int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path)
 }
 
 int astre_gpu_global_offsets_dev(astre_gpu_ctx *ctx, const uint32_t *all_counts_dev, uint32_t world_size, uint32_t rank,
-                                 uint32_t n_views, uint64_t *offsets_dev, uint64_t *view_totals_dev, void *stream)
+                                 uint32_t n_views, uint32_t rank_major, uint64_t *offsets_dev, uint64_t *view_totals_dev,
+                                 void *stream)
 {
     if (!ctx || !all_counts_dev || world_size == 0 || rank >= world_size) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "bad argument") : ASTRE_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    k_global_offsets<<<1, 256, 0, s>>>(all_counts_dev, world_size, rank, n_views,
+    k_global_offsets<<<1, 256, 0, s>>>(all_counts_dev, world_size, rank, n_views, rank_major,
                                        reinterpret_cast<unsigned long long *>(offsets_dev),
                                        reinterpret_cast<unsigned long long *>(view_totals_dev));
     CK_LAUNCH();
@@ -1678,6 +1689,20 @@ void astre_global_offsets(const uint32_t *all_counts, uint32_t world_size, uint3
         }
         if (view_totals) view_totals[v] = total;
         run += total;
+    }
+}
+
+void astre_global_offsets_rank_major(const uint32_t *all_counts, uint32_t world_size, uint32_t rank, uint32_t n_units,
+                                     uint64_t *offsets, uint64_t *segment_len)
+{
+    uint64_t run = 0;
+    for (uint32_t r = 0; r < rank && r < world_size; ++r)
+        for (uint32_t u = 0; u < n_units; ++u) run += all_counts[(size_t)r * n_units + u];
+    for (uint32_t u = 0; u < n_units; ++u) {
+        const uint64_t c = all_counts[(size_t)rank * n_units + u];
+        if (offsets) offsets[u] = run;
+        if (segment_len) segment_len[u] = c;
+        run += c;
     }
 }
 

@@ -296,6 +296,9 @@ k_frame_fused(const FrameParams P, const __grid_constant__ ViewSet VS, const __g
 
     KeySink sink{ kbuf, 0u, &P, &bp, lane };
     uint32_t parity = 0;
+    // Programmatic dependent launch (single-range launches): everything above overlaps the tail of the frame's
+    // reset kernel; nothing that kernel writes (work counters, key total, counts, bins) is touched before here.
+    cudaGridDependencySynchronize();
 
     for (uint32_t level = 0; level < LT.n; ++level) {
     const uint32_t first = LT.first[level], end = LT.end[level];

@@ -225,22 +225,38 @@ k_run_write(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t cl
 // One block (the table is tiny: n_views <= worlds x views of one shard).
 __global__ void __launch_bounds__(256)
 k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, uint32_t rank, uint32_t n_views,
-                 unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
+                 uint32_t rank_major, unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
 {
     __shared__ unsigned long long s_warp[8];
     __shared__ unsigned long long s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
+    if (rank_major) {
+        // whole-world shards: everything of the earlier ranks comes first, then this rank's units in order
+        unsigned long long mine = 0;
+        for (size_t i = threadIdx.x; i < (size_t)rank * n_views; i += 256u) mine += all_counts[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if (lane == 0) s_warp[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_carry = t; }
+        __syncthreads();
+    }
     for (uint32_t base = 0; base < n_views; base += 256u) {
         const uint32_t v = base + threadIdx.x;
         unsigned long long total = 0, before = 0;
-        if (v < n_views)
-            for (uint32_t r = 0; r < world_size; ++r) {
-                const unsigned long long c = all_counts[(size_t)r * n_views + v];
-                if (r < rank) before += c;
-                total += c;
+        if (v < n_views) {
+            if (rank_major) {
+                total = all_counts[(size_t)rank * n_views + v];
+            } else {
+                for (uint32_t r = 0; r < world_size; ++r) {
+                    const unsigned long long c = all_counts[(size_t)r * n_views + v];
+                    if (r < rank) before += c;
+                    total += c;
+                }
             }
+        }
         unsigned long long incl = total;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }

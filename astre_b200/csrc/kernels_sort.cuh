@@ -169,6 +169,44 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
     return v;
 }
 
+// Exclusive scan of counts[0..n) into offsets[0..n] (offsets[n] = total) by one block of 256 threads.
+__device__ __forceinline__ void scan_counts_block(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets,
+                                                  const uint32_t n, unsigned long long *s_warp8)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t per = (n + 255u) / 256u;
+    const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += counts[i];
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp8[warp] = incl;
+    __syncthreads();
+    unsigned long long off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { if (w < warp) off += s_warp8[w]; total += s_warp8[w]; }
+    unsigned long long run = off + incl - sum;
+    for (uint32_t i = lo; i < hi; ++i) { offsets[i] = run; run += counts[i]; }
+    if (threadIdx.x == 0) offsets[n] = total;
+    __syncthreads();
+}
+
+// Frames that do not sort in the same call: the scan of the per-view counts as its own launch
+// (sorted frames get it from block 0 of k_sort_lsd_all).  Also leaves the key total in `hint`.
+__global__ void __launch_bounds__(256)
+k_scan_counts(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n,
+              const FrameControl *ctl, unsigned long long *hint)
+{
+    __shared__ unsigned long long s_warp[8];
+    cudaGridDependencySynchronize();
+    if (threadIdx.x == 0 && hint) *hint = ctl->key_total;
+    scan_counts_block(counts, offsets, n, s_warp);
+}
+
 // ---- bucket sort ------------------------------------------------------------------------------------------
 
 // Exclusive scan of the bins in place (bins[d] becomes the start of bucket d = the scatter's cursor), the
@@ -298,13 +336,16 @@ k_bin_scatter(const unsigned long long *__restrict__ in, unsigned long long *__r
 __global__ void __launch_bounds__(256)
 k_bin_rank(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out, const uint32_t *__restrict__ cursor,
            const uint32_t *__restrict__ chunk_first, const __grid_constant__ BinPlan bp, SortControl *sc,
-           const FrameControl *ctl, const unsigned long long cap, const uint32_t force_lsd)
+           const FrameControl *ctl, const unsigned long long cap, const uint32_t force_lsd, unsigned long long *hint)
 {
     __shared__ unsigned long long s_keys[kRankSmemKeys];
     cudaGridDependencySynchronize();
     const uint32_t n = sort_key_count(ctl, cap);
     if (sort_takes_fallback(sc, n, force_lsd)) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->result_buf = 0u; sc->path = kSortBins; sc->n_keys = n; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc->result_buf = 0u; sc->path = kSortBins; sc->n_keys = n;
+        if (hint) *hint = ctl->key_total;      // mapped host word (next frame's bucket count); the PCIe write overlaps the ranking
+    }
     const uint32_t n_chunks = n / kChunkKeys + 1u;                    // chunk c exists while 1024 c <= n
     for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const uint32_t d0 = chunk_first[c];
@@ -315,13 +356,24 @@ k_bin_rank(const unsigned long long *__restrict__ in, unsigned long long *__rest
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < m; i += 256u) s_keys[i] = in[lo + i];
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < m; i += 256u) {
-            const unsigned long long key = s_keys[i];
-            const uint32_t d = bin_digit(bp, key);
-            const uint32_t bs = (d ? __ldg(cursor + d - 1u) : 0u) - lo, be = __ldg(cursor + d) - lo;
-            uint32_t r = 0;
-            for (uint32_t j = bs; j < be; ++j) r += s_keys[j] < key ? 1u : 0u;
-            out[lo + bs + r] = key;
+        for (uint32_t i0 = threadIdx.x; i0 < m; i0 += 4u * 256u) {
+            // four keys per thread and round: their bucket bounds (L2 round trips) are fetched together
+            unsigned long long key[4];
+            uint32_t bs[4], be[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t i = i0 + q * 256u;
+                key[q] = i < m ? s_keys[i] : 0ull;
+                const uint32_t d = bin_digit(bp, key[q]);
+                bs[q] = i < m ? (d ? __ldg(cursor + d - 1u) : 0u) - lo : 0u;
+                be[q] = i < m ? __ldg(cursor + d) - lo : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t r = 0;
+                for (uint32_t j = bs[q]; j < be[q]; ++j) r += s_keys[j] < key[q] ? 1u : 0u;
+                if (i0 + q * 256u < m) out[lo + bs[q] + r] = key[q];
+            }
         }
     }
 }
@@ -383,7 +435,9 @@ __device__ __forceinline__ void sort_grid_barrier(uint32_t *counter, uint32_t ta
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__restrict__ buf1, SortControl *sc,
                unsigned long long *__restrict__ lookback, const __grid_constant__ SortPlan plan, const FrameControl *ctl,
-               const unsigned long long cap, const uint32_t force_lsd)
+               const unsigned long long cap, const uint32_t force_lsd,
+               const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n_counts,
+               unsigned long long *hint)
 {
     constexpr int THREADS = kSortThreads, ITEMS = 8;
     constexpr int kTile = THREADS * ITEMS;
@@ -394,7 +448,10 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
     __shared__ unsigned long long s_keys[kTile];
     cudaGridDependencySynchronize();
     const uint32_t n = sort_key_count(ctl, cap);
+    // the frame's last launch: block 0 also scans the per-(world, view) counts into list offsets
+    if (blockIdx.x == 0 && n_counts) scan_counts_block(counts, offsets, n_counts, s_keys);
     if (!sort_takes_fallback(sc, n, force_lsd)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hint) *hint = ctl->key_total;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -564,35 +621,6 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
         sort_grid_barrier(&sc->lsd_barrier, ++round * gridDim.x);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { sc->result_buf = executed & 1u; sc->path = kSortLsd; }
-}
-
-// Exclusive scan of counts[0..n) into offsets[0..n] (offsets[n] = total).  One block of 256.
-// Also leaves the frame's key total in `hint` (mapped host memory): next frame's bucket count.
-__global__ void __launch_bounds__(256)
-k_scan_counts(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n,
-              const FrameControl *ctl, unsigned long long *hint)
-{
-    __shared__ unsigned long long s_warp[8];
-    cudaGridDependencySynchronize();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t per = (n + 255u) / 256u;
-    const uint32_t lo = min(threadIdx.x * per, n), hi = min(lo + per, n);
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; ++i) sum += counts[i];
-    unsigned long long incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned long long off = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { if (w < warp) off += s_warp[w]; total += s_warp[w]; }
-    unsigned long long run = off + incl - sum;
-    for (uint32_t i = lo; i < hi; ++i) { offsets[i] = run; run += counts[i]; }
-    if (threadIdx.x == 0) { offsets[n] = total; if (hint) *hint = ctl->key_total; }
 }
 
 }  // namespace astre

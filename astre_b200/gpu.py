@@ -33,6 +33,7 @@ def make_flags(visible, phases):
 class GpuContext:
     def __init__(self, max_entities, max_views=8, max_keys=0, device=0):
         self._lib = load_library()
+        self.bound_stream = None      # cudaStream_t the context enqueues on (None: its own non-blocking stream)
         self._h = self._lib.astre_gpu_create(int(device), int(max_entities), int(max_views), int(max_keys))
         if not self._h:
             raise AstreError(-1, self._lib.astre_gpu_last_error(None).decode())
@@ -136,10 +137,10 @@ class GpuContext:
         self._check(self._lib.astre_gpu_last_sort_path(self._h, C.byref(v)))
         return int(v.value)
 
-    def global_offsets_dev(self, all_counts_ptr, world_size, rank, n_views, offsets_ptr, totals_ptr=0, stream=None):
+    def global_offsets_dev(self, all_counts_ptr, world_size, rank, n_views, offsets_ptr, totals_ptr=0, stream=None, rank_major=False):
         """Segment offsets of this rank from an all-gathered count table, all in device memory (stream-ordered)."""
         self._check(self._lib.astre_gpu_global_offsets_dev(self._h, int(all_counts_ptr), int(world_size), int(rank), int(n_views),
-                                                           int(offsets_ptr) or None, int(totals_ptr) or None, stream))
+                                                           1 if rank_major else 0, int(offsets_ptr) or None, int(totals_ptr) or None, stream))
 
     def sync(self):
         self._check(self._lib.astre_gpu_sync(self._h))
@@ -147,6 +148,7 @@ class GpuContext:
     def set_stream(self, stream):
         """stream: a cudaStream_t handle as int (e.g. torch.cuda.current_stream().cuda_stream) or None."""
         self._check(self._lib.astre_gpu_set_stream(self._h, C.c_void_p(stream) if stream else None))
+        self.bound_stream = int(stream) if stream else None
 
     @property
     def launch_count(self):
@@ -351,11 +353,13 @@ def ortho_view_matrix(eye, center, up, l, r, b, t, n, f):
     return clip
 
 
-def global_offsets(all_counts, rank):
-    """all_counts [world_size, n_views] -> (offsets[n_views] of this rank, totals[n_views])."""
+def global_offsets(all_counts, rank, rank_major=False):
+    """all_counts [world_size, n_views] -> (offsets[n_views] of this rank, totals[n_views]).
+    rank_major: whole-world shards (the global list is the concatenation of the ranks' lists); totals = own segment lengths."""
     lib = load_library()
     a = np.ascontiguousarray(all_counts, dtype=np.uint32)
     ws, nv = a.shape
     off, tot = np.zeros(nv, np.uint64), np.zeros(nv, np.uint64)
-    lib.astre_global_offsets(_ptr(a, C.c_uint32), ws, int(rank), nv, _ptr(off, C.c_uint64), _ptr(tot, C.c_uint64))
+    fn = lib.astre_global_offsets_rank_major if rank_major else lib.astre_global_offsets
+    fn(_ptr(a, C.c_uint32), ws, int(rank), nv, _ptr(off, C.c_uint64), _ptr(tot, C.c_uint64))
     return off, tot

@@ -68,11 +68,11 @@ def exchange_counts(counts, group=None):
     return out.reshape(ws, -1)
 
 
-def segment_offsets(all_counts, rank):
-    """Offset of `rank`'s segment of every view in the global draw list, which is ordered
-    (view, rank, key), and the per-view totals."""
+def segment_offsets(all_counts, rank, rank_major=False):
+    """Offset of `rank`'s segment of every view in the global draw list -- ordered (view, rank, key) for flat scenes
+    sharded by entity range, rank-major (= world-major) for batched worlds sharded by whole worlds -- and the totals."""
     a = all_counts.detach().cpu().numpy().astype(np.uint32)
-    return _gpu.global_offsets(a, rank)
+    return _gpu.global_offsets(a, rank, rank_major)
 
 
 def device_view(ptr, n, typestr, device):
@@ -80,6 +80,64 @@ def device_view(ptr, n, typestr, device):
     class _View:
         __cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(_View(), device=device)
+
+
+class CountExchange:
+    """The per-frame exchange of SURVEY.md 8e, kept OFF the frame's critical path.
+
+    Per frame, on the frame's stream: one tiny copy of the shard's per-view counts into a staging slot (the
+    library zeroes its counters when the next frame begins).  Everything else runs on a side stream while the
+    next frames compute: NCCL all-gather of the staged counts -> [world_size, n_views] table ->
+    astre_gpu_global_offsets_dev (this rank's segment offsets and the per-view totals, on the device).
+    Two slots alternate; a slot is reused only after its exchange has finished (an event wait that is already
+    satisfied in steady state).  `finish()` joins the side stream back (end of a timed region, or before reading).
+    No host round trip anywhere."""
+
+    def __init__(self, ctx, n_counts, group=None, device=None, rank_major=False):
+        self.ctx, self.group, self.n, self.rank_major = ctx, group, int(n_counts), bool(rank_major)
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.counts_dev = device_view(ctx.device_counts_ptr(), self.n, "<i4", self.device)
+        self.stage = [torch.zeros(self.n, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.table = [torch.zeros((self.world, self.n), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.offsets = [torch.zeros(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.totals = [torch.zeros(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=self.device)
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.frame = 0
+
+    def enqueue(self):
+        """Call right after the frame's cull (counts final) on the frame's stream."""
+        p = self.frame & 1
+        main = torch.cuda.current_stream(self.device)
+        if self.frame >= 2:
+            main.wait_event(self.done[p])                       # slot p: exchange of frame-2 finished
+        self.stage[p].copy_(self.counts_dev, non_blocking=True)
+        self.staged[p].record(main)
+        self.side.wait_event(self.staged[p])
+        with torch.cuda.stream(self.side):
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.table[p].view(-1), self.stage[p], group=self.group)
+            else:
+                self.table[p].view(-1).copy_(self.stage[p], non_blocking=True)
+            self.ctx.global_offsets_dev(self.table[p].data_ptr(), self.world, self.rank, self.n,
+                                        self.offsets[p].data_ptr(), self.totals[p].data_ptr(), self.side.cuda_stream,
+                                        rank_major=self.rank_major)
+            self.done[p].record(self.side)
+        self.frame += 1
+        return p
+
+    def finish(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+
+    def last(self):
+        """(all_counts [world, n], offsets [n], totals [n]) of the most recent frame, on the host (synchronises)."""
+        p = (self.frame - 1) & 1
+        self.done[p].synchronize()
+        return (self.table[p].cpu().numpy().astype(np.uint32), self.offsets[p].cpu().numpy().astype(np.uint64),
+                self.totals[p].cpu().numpy().astype(np.uint64))
 
 
 class GlobalDrawList:
@@ -108,6 +166,7 @@ class GlobalDrawList:
         self._gathered = None
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._epoch = 0
+        self._bind()
         if mode == "p2p" and self.world > 1:
             mine = [self.max_keys, ctx.export_handle(0), ctx.export_handle(1)]
             handles = [None] * self.world
@@ -119,11 +178,22 @@ class GlobalDrawList:
                 if r != self.rank:
                     self.peer[r] = [ctx.import_handle(handles[r][1]), ctx.import_handle(handles[r][2])]
 
+    def _bind(self):
+        """The collectives below are issued by torch on ITS current stream; the flow is only correct if the library's
+        frame, publish and merge kernels are ordered on that same stream.  Bind the context to it (a change of
+        stream synchronises the old one, so work already enqueued stays ordered)."""
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        if self.ctx.bound_stream != cur:
+            self.ctx.set_stream(cur)
+        return cur
+
     def build_enqueue(self, frame_index, sliced=False, out_cap=0, stream=None):
         """Peer-to-peer flow with the key counts left on the device: nothing here waits for the GPU, so frames
         and merges can be enqueued back to back.  The list is in the library's merge buffers afterwards
         (ctx.merged_count() / ctx.read_merged synchronise)."""
         assert self.mode == "p2p" or self.world == 1
+        cur = self._bind()
+        assert stream in (None, cur), "pass the torch current stream (or None): the NCCL calls run on it"
         parity = frame_index & 1
         self.ctx.publish_keys(parity, stream)
         self._all_counts = exchange_counts(self.counts_dev, self.group)          # [G, F] int32, stays on the device
@@ -138,6 +208,7 @@ class GlobalDrawList:
         over NVLink by the library's own kernels.  Call once per frame on every rank (after ctx.frame());
         the epoch counter lives here and must advance in step on all ranks."""
         assert self.mode == "p2p" or self.world == 1
+        self._bind()
         self._epoch += 1
         p0 = [self.peer[r][0] for r in range(self.world)]
         p1 = [self.peer[r][1] for r in range(self.world)]
@@ -147,6 +218,8 @@ class GlobalDrawList:
         """Call after ctx.frame().  Returns (all_counts [G, F] on the host, out_first, out_count): the
         merged keys / sources of positions [out_first, out_first + out_count) are in the library's
         merge buffers (ctx.read_merged / ctx.device_merged_ptrs)."""
+        cur = self._bind()
+        assert stream in (None, cur), "pass the torch current stream (or None): the NCCL calls run on it"
         parity = frame_index & 1
         self.ctx.publish_keys(parity, stream)
         # the counts all-gather is stream-ordered after the publish copy on every rank: once it has

@@ -339,11 +339,16 @@ ASTRE_API void astre_ortho_view_matrix(const float *eye3, const float *center3, 
  * all_counts is [world_size][n_views]; offsets/view_totals are [n_views]. */
 ASTRE_API void astre_global_offsets(const uint32_t *all_counts, uint32_t world_size, uint32_t rank,
                                     uint32_t n_views, uint64_t *offsets, uint64_t *view_totals);
+/* Batched worlds sharded by WHOLE WORLDS: unit u of rank r is (world, view) number u of that rank's worlds, and
+ * the global list is the rank-major concatenation of the ranks' lists (= world-major):
+ * offsets[u] = keys of all earlier ranks + keys of this rank's earlier units; segment_len[u] = all_counts[rank][u]. */
+ASTRE_API void astre_global_offsets_rank_major(const uint32_t *all_counts, uint32_t world_size, uint32_t rank,
+                                               uint32_t n_units, uint64_t *offsets, uint64_t *segment_len);
 /* The same on the device and stream-ordered, for an all-gathered count table that never leaves the GPU
  * (all pointers are device pointers; offsets_dev / view_totals_dev may be NULL): the per-frame exchange of
- * SURVEY.md 8e then needs no host round trip.  stream: cudaStream_t cast to void* (NULL = the context's). */
+ * SURVEY.md 8e then needs no host round trip.  rank_major != 0: the layout of astre_global_offsets_rank_major.  stream: cudaStream_t cast to void* (NULL = the context's). */
 ASTRE_API int astre_gpu_global_offsets_dev(astre_gpu_ctx *ctx, const uint32_t *all_counts_dev, uint32_t world_size,
-                                           uint32_t rank, uint32_t n_views, uint64_t *offsets_dev,
+                                           uint32_t rank, uint32_t n_views, uint32_t rank_major, uint64_t *offsets_dev,
                                            uint64_t *view_totals_dev, void *stream);
 
 #ifdef __cplusplus

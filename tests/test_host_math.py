@@ -46,3 +46,24 @@ def test_ortho_view_matches_oracle(oracle):
     got = gpu.ortho_view_matrix(eye, center, up, -30, 30, -20, 20, 0.1, 200.0)
     exp = oracle.mat4_mul(oracle.ortho(-30, 30, -20, 20, 0.1, 200.0), oracle.look_at(eye, center, up))
     assert np.array_equal(oracle_lib.bits(got), oracle_lib.bits(exp))
+
+
+def test_oracle_backed_view_builder_matches_the_product(oracle):
+    """bench.py's reference arm builds the synthetic views with the oracle so that its process never maps the product
+    library; both builders must give the same clip matrices bit for bit."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from astre_b200 import scenes
+    a = scenes.config3(16)
+    a5 = scenes.config5(n_worlds=8, entities_per_world=16)
+    scenes.set_matrix_provider(bench.OracleMatrices)
+    try:
+        b = scenes.config3(16)
+        b5 = scenes.config5(n_worlds=8, entities_per_world=16)
+    finally:
+        scenes.set_matrix_provider(None)
+    assert np.array_equal(a.clip.view(np.uint32), b.clip.view(np.uint32))
+    assert np.array_equal(a5.clip.view(np.uint32), b5.clip.view(np.uint32))

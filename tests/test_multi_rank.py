@@ -37,7 +37,7 @@ def _worker(rank, world_size, port, kind, out_dir):
             assert shard.n_worlds == whi - wlo
         _, keys, counts = oracle.frame(shard)                 # stand-in for the rank's GPU frame
         all_counts = multi.exchange_counts(torch.from_numpy(counts.astype(np.int32)))
-        offsets, totals = multi.segment_offsets(all_counts, rank)
+        offsets, totals = multi.segment_offsets(all_counts, rank, rank_major=(kind != "flat"))
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), keys=keys, counts=counts, offsets=offsets, totals=totals,
                  all_counts=all_counts.numpy())
     finally:
@@ -95,7 +95,11 @@ def test_world_shards(tmp_path, oracle):
     _, ref_keys, ref_counts = oracle.frame(scene)
     got = np.concatenate([r["counts"] for r in res])
     assert np.array_equal(got, ref_counts)                      # worlds [0,4) on rank 0, [4,8) on rank 1
-    assert int(res[1]["offsets"][0]) == int(res[0]["counts"].sum()) or True
+    # whole-world shards: the global list is the concatenation of the ranks' lists (rank-major = world-major)
+    n0 = int(res[0]["counts"].sum())
+    assert res[0]["offsets"].tolist() == np.concatenate([[0], np.cumsum(res[0]["counts"])[:-1]]).tolist()
+    assert res[1]["offsets"].tolist() == (n0 + np.concatenate([[0], np.cumsum(res[1]["counts"])[:-1]])).tolist()
+    assert np.array_equal(res[1]["totals"], res[1]["counts"])                 # segment lengths
     # a shard numbers its worlds from 0: shift the world field back and compare with the unsharded list
     wb_shard, wb_full = 2, 3
     rebuilt = []
@@ -116,6 +120,10 @@ def test_shard_helpers():
     a = torch.tensor([[3, 1], [2, 5], [0, 7]], dtype=torch.int32)
     off, tot = multi.segment_offsets(a, 2)
     assert tot.tolist() == [5, 13] and off.tolist() == [5, 5 + 6]
+    off, seg = multi.segment_offsets(a, 2, rank_major=True)
+    assert off.tolist() == [11, 11] and seg.tolist() == [0, 7]
+    off, seg = multi.segment_offsets(a, 1, rank_major=True)
+    assert off.tolist() == [4, 6] and seg.tolist() == [2, 5]
 
 
 def test_shard_subtrees_partition_properties():

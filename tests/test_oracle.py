@@ -213,3 +213,53 @@ def test_trs_matrix_conventions_against_scipy(oracle):
         rot = Rotation.from_quat(q)
         assert np.allclose(f, rot.apply([0, 0, -1]), atol=1e-6) and np.allclose(u, rot.apply([0, 1, 0]), atol=1e-6)
         assert np.allclose(r, rot.apply([1, 0, 0]), atol=1e-6)
+
+
+def test_box_pretest_only_removes_what_lies_outside_the_view_volume(oracle):
+    """The cull spec's box pre-test against the plain six-plane test of SURVEY Appendix B:
+    (a) box + planes keeps a SUBSET of planes-only; (b) every entity the box removes is outside the view volume --
+    checked in float64 against the exact box of the volume's eight corners, not the widened float box the spec uses."""
+    import ctypes as C
+    s = scenes.config3(400_000)
+    s.pos = (s.pos * np.float32(0.1)).astype(np.float32)            # +-200 around the camera: many borderline entities
+    s.scale = (s.scale * np.float32(3.0)).astype(np.float32)         # big bounds: plane-test false positives beyond the corners
+    world = oracle.transform_flat(s.pos, s.rot, s.scale)
+    F = s.views_per_world
+    keys_box, counts_box = oracle.cull_keys(world, s.mesh, s.shader, s.flags, s.bounds, s.clip, s.masks)
+    # planes only: the same views with an unbounded box
+    brecs, nb = oracle.make_bounds(s.bounds)
+    vrecs = oracle.make_views(s.clip, s.masks)
+    for v in range(F):
+        for i in range(3):
+            vrecs[v].lo[i], vrecs[v].hi[i] = -np.inf, np.inf
+    cap = s.n * F
+    keys = np.empty(cap, np.uint64)
+    counts = np.zeros(F, np.uint32)
+    p = oracle_lib._p
+    total = oracle.lib.orc_cull_keys(C.c_uint32(s.n), p(world, C.c_float), p(s.mesh, C.c_uint32), p(s.shader, C.c_uint32),
+                                     p(s.flags, C.c_uint8), brecs, C.c_uint32(nb), C.c_uint32(1), C.c_uint32(0), C.c_uint32(F), vrecs,
+                                     p(keys, C.c_uint64), C.c_uint64(cap), p(counts, C.c_uint32))
+    keys_planes = oracle.sort_keys(keys[:total])
+    assert np.all(counts_box <= counts)
+    removed = np.setdiff1d(keys_planes, keys_box, assume_unique=True)
+    assert len(np.setdiff1d(keys_box, keys_planes, assume_unique=True)) == 0          # (a) subset
+    assert len(removed) > 50, "the scene must contain entities only the box removes"
+
+    # (b) float64 geometry: the exact corner box of each view volume, and each removed entity's bounds box
+    w64 = world.astype(np.float64).reshape(-1, 4, 4)                                   # [n, column, row]
+    bnd = s.bounds.astype(np.float64)
+    for key in removed:
+        v = int(key >> np.uint64(59)) & 31
+        slot = int(key & np.uint64((1 << 26) - 1))
+        clip = s.clip[0, v].astype(np.float64).reshape(4, 4).T                         # math layout [row, col]
+        corners = np.array([[x, y, z, 1.0] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)])
+        pts = (np.linalg.inv(clip) @ corners.T).T
+        pts = pts[:, :3] / pts[:, 3:4]
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        m = w64[slot]
+        b = bnd[s.mesh[slot]]
+        c = m[0, :3] * b[0] + m[1, :3] * b[1] + m[2, :3] * b[2] + m[3, :3]
+        e = np.abs(m[0, :3]) * b[3] + np.abs(m[1, :3]) * b[4] + np.abs(m[2, :3]) * b[5]
+        r = b[6] * np.sqrt(max((m[j, :3] ** 2).sum() for j in range(3)))
+        t = e + r
+        assert np.any(c + t < lo) or np.any(c - t > hi), (hex(int(key)), c, t, lo, hi)
