@@ -62,6 +62,7 @@ SIGNATURES = {
     "astre_gpu_read_keys": (C.c_int, [_P, C.c_uint32, C.c_uint32, _U64, C.c_uint64, _U64]),
     "astre_gpu_read_all_keys": (C.c_int, [_P, _U64, C.c_uint64, _U64]),
     "astre_gpu_read_visible_world": (C.c_int, [_P, C.c_uint64, C.c_uint64, _F]),
+    "astre_gpu_read_draw_list": (C.c_int, [_P, _U64, _F, C.c_uint64, _U64]),
     "astre_gpu_read_runs": (C.c_int, [_P, C.POINTER(DrawRun), C.c_uint32, _U32]),
     "astre_gpu_slot_entity": (C.c_int, [_P, C.c_uint32, _U64]),
     "astre_gpu_device_world": (_P, [_P]),

@@ -36,6 +36,16 @@ struct Level {
 
 }  // namespace
 
+namespace {
+// What a frame launches, decided on the host before anything is enqueued.
+struct FramePlan {
+    uint32_t stage_flags, n, n_counts;
+    bool cull, sort, sort_now;
+    SortPlan plan;      // LSD fallback digits
+    BinPlan bp;         // bucket digit
+};
+}  // namespace
+
 struct astre_gpu_ctx {
     int device = 0;
     int sm_count = 148;
@@ -66,8 +76,8 @@ struct astre_gpu_ctx {
     uint32_t *d_bins = nullptr;           // key sort: bucket counts -> bucket starts -> bucket ends (kernels_sort.cuh)
     uint32_t cap_bin_bits = 0;            // log2 of the bins allocated
     uint32_t *d_chunk_first = nullptr;    // key sort: first bucket of every 1024-key chunk
-    unsigned long long *h_hint = nullptr; // mapped host word: key total of the last finished frame (sizes the next frame's buckets)
-    unsigned long long *d_hint = nullptr;
+    FrameResultHost *h_res = nullptr;     // mapped host block the frame's last launch writes: key total (also the hint that sizes
+    FrameResultHost *d_res = nullptr;     // the next frame's buckets), sort outcome, counts and offsets -- read after one sync, no copy
     uint32_t force_lsd = 0;               // ASTRE_SORT_FORCE_LSD=1: always take the LSD fallback (tests)
     int bin_bits_override = -1;           // ASTRE_SORT_BIN_BITS=n: fixed bucket-digit width (tests)
     uint32_t claim_groups = 8;            // work counters of the fused kernel in a flat frame (ASTRE_CLAIM_GROUPS; 0 = per-CTA shared counters)
@@ -80,7 +90,16 @@ struct astre_gpu_ctx {
     uint32_t cap_heads = 0;
     uint32_t *d_head_counts = nullptr;   // run heads per CTA of k_run_count, then their exclusive scan (+ total)
     uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
-    uint32_t epoch = 0;
+    uint32_t epoch = 0;                  // host mirror of SortControl::epoch (one step per frame)
+    uint32_t last_want_bits = 0;         // bucket-digit width of the last plan (hysteresis)
+
+    // ASTRE_FRAME_GRAPH: the frame's launches as one instantiated CUDA graph
+    cudaGraphExec_t graph_exec = nullptr;
+    FramePlan graph_plan;
+    uint64_t graph_views_version = 0, graph_levels_version = 0, views_version = 1, levels_version = 1;
+    cudaStream_t graph_stream = nullptr;
+    uint32_t graph_launches = 0, graph_captures = 0;
+    bool last_timed = false;             // the last frame recorded the cull events (not when replayed from a graph)
 
     // f3: global draw list across GPUs
     unsigned char *d_publish[2] = {nullptr, nullptr};        // keys | samples | cut table at a fixed address: what peers map
@@ -195,13 +214,17 @@ FrameParams params_of(const astre_gpu_ctx *c, bool cull)
     return P;
 }
 
-__global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts, uint32_t epoch,
+constexpr uint32_t kEpochWrap = 1u << 27;    // look-back tags hold 27 bits of frame number (x 8 passes + 1 in 30 bits)
+
+__global__ void k_frame_begin(FrameControl *ctl, SortControl *sc, uint32_t *counts, uint32_t n_counts,
                               uint32_t *bins, uint32_t n_bins)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         ctl->key_total = 0; ctl->overflow = 0; ctl->barrier = 0;
-        sc->n_keys = 0; sc->epoch = epoch;
+        sc->n_keys = 0;
+        const uint32_t e = sc->epoch + 1u;             // the host keeps a mirror and clears the tagged words at the wrap
+        sc->epoch = e >= kEpochWrap ? 1u : e;
         sc->max_bucket = 0; sc->scan_ticket = 0; sc->sum_sq = 0; sc->lsd_barrier = 0; sc->result_buf = 0; sc->path = kSortNone;
     }
     if (tid < kSortPasses) { sc->skip[tid] = 1; sc->tile_counter[tid] = 0; }
@@ -249,6 +272,7 @@ int rebuild_levels(astre_gpu_ctx *ctx)
     const uint32_t n = ctx->n_entities;
     ctx->levels.clear();
     ctx->has_parents = false;
+    ++ctx->levels_version;
     for (uint32_t i = 0; i < n; ++i)
         if (ctx->h_parent[i] != ASTRE_NO_PARENT) { ctx->has_parents = true; break; }
     ctx->hier_dirty = false;
@@ -299,22 +323,24 @@ int cache_results(astre_gpu_ctx *ctx)
     if (ctx->results_cached) return ASTRE_OK;
     cudaStream_t s = ctx->last_stream;
     const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
-    FrameControl ctl;
     CK(cudaStreamSynchronize(s));
-    CK(cudaMemcpy(&ctl, ctx->d_ctl, sizeof ctl, cudaMemcpyDeviceToHost));
-    uint32_t result_buf = 0;
-    if (ctx->last_sorted)          // which key buffer the sort ended in is decided on the device
-        CK(cudaMemcpy(&result_buf, &ctx->d_sc->result_buf, sizeof result_buf, cudaMemcpyDeviceToHost));
+    // the frame's last launch left everything in mapped host memory (counts and offsets too, unless there are many)
+    const FrameResultHost &R = *ctx->h_res;
     ctx->h_counts.assign(n_counts, 0);
     ctx->h_offsets.assign((size_t)n_counts + 1, 0);
     if (n_counts) {
-        CK(cudaMemcpy(ctx->h_counts.data(), ctx->d_counts, (size_t)n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(ctx->h_offsets.data(), ctx->d_offsets, ((size_t)n_counts + 1) * sizeof(unsigned long long),
-                      cudaMemcpyDeviceToHost));
+        if (R.n_counts == n_counts) {
+            std::memcpy(ctx->h_counts.data(), R.counts, (size_t)n_counts * sizeof(uint32_t));
+            std::memcpy(ctx->h_offsets.data(), R.offsets, ((size_t)n_counts + 1) * sizeof(unsigned long long));
+        } else {
+            CK(cudaMemcpy(ctx->h_counts.data(), ctx->d_counts, (size_t)n_counts * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ctx->h_offsets.data(), ctx->d_offsets, ((size_t)n_counts + 1) * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost));
+        }
     }
-    ctx->h_total = ctl.key_total;
-    ctx->h_overflow = (ctl.key_total > ctx->max_keys) ? 1u : ctl.overflow;
-    ctx->h_result_buf = result_buf;
+    ctx->h_total = n_counts ? R.key_total : 0ull;        // a frame without views emits no keys and publishes nothing
+    ctx->h_overflow = n_counts ? ((R.key_total > ctx->max_keys) ? 1u : R.overflow) : 0u;
+    ctx->h_result_buf = ctx->last_sorted ? R.result_buf : 0u;
     ctx->results_cached = true;
     ctx->results_cached_total_valid = true;
     return ASTRE_OK;
@@ -416,9 +442,10 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     while (ctx->cap_bin_bits < kMaxBinBits && (1ull << ctx->cap_bin_bits) * 4ull < ctx->max_keys) ++ctx->cap_bin_bits;
     CKC(cudaMalloc(&ctx->d_bins, (size_t)(1u << ctx->cap_bin_bits) * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_chunk_first, (size_t)(ctx->max_keys / kChunkKeys + 2) * sizeof(uint32_t)));
-    CKC(cudaHostAlloc(&ctx->h_hint, sizeof(unsigned long long), cudaHostAllocMapped));
-    *ctx->h_hint = ~0ull;                                            // no frame has finished yet
-    CKC(cudaHostGetDevicePointer(&ctx->d_hint, ctx->h_hint, 0));
+    CKC(cudaHostAlloc(&ctx->h_res, sizeof(FrameResultHost), cudaHostAllocMapped));
+    std::memset(ctx->h_res, 0, sizeof(FrameResultHost));
+    ctx->h_res->key_total = ~0ull;                                   // no frame has finished yet
+    CKC(cudaHostGetDevicePointer(&ctx->d_res, ctx->h_res, 0));
     if (std::getenv("ASTRE_SORT_FORCE_LSD")) ctx->force_lsd = 1u;
     if (const char *m = std::getenv("ASTRE_SORT_BIN_BITS")) ctx->bin_bits_override = std::atoi(m);
     {
@@ -482,7 +509,8 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    if (ctx->h_hint) cudaFreeHost(ctx->h_hint);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     delete ctx;
 }
 
@@ -645,6 +673,7 @@ int astre_gpu_set_mesh_bounds(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->n_meshes = n_meshes;
+    ++ctx->views_version;
     return ASTRE_OK;
 }
 
@@ -687,6 +716,7 @@ int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t en
     if (n_rec) CK(cudaMemcpy(ctx->d_views, recs.data(), n_rec * sizeof(ViewDev), cudaMemcpyHostToDevice));
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     if (n_worlds == 1 && views_per_world) std::memcpy(ctx->h_viewset.v, recs.data(), views_per_world * sizeof(ViewDev));
+    ++ctx->views_version;                         // a captured frame graph has the old records and pointers baked in
     ctx->n_worlds = n_worlds;
     ctx->entities_per_world = n_worlds > 1 ? entities_per_world : 0;
     ctx->views_per_world = views_per_world;
@@ -722,69 +752,32 @@ static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &pl
                           (const SortControl *)ctx->d_sc, ctl, cap, ctx->force_lsd));
     CK_LAUNCH();
     CK(cudaLaunchKernelEx(&cfg, k_bin_rank, (const unsigned long long *)ctx->d_keys[1], ctx->d_keys[0], (const uint32_t *)ctx->d_bins,
-                          (const uint32_t *)ctx->d_chunk_first, bp, ctx->d_sc, ctl, cap, ctx->force_lsd, ctx->d_hint));
+                          (const uint32_t *)ctx->d_chunk_first, bp, ctx->d_sc, ctl, cap, ctx->force_lsd));
     CK_LAUNCH();
     cfg.gridDim = dim3((unsigned)ctx->sort_grid); cfg.blockDim = dim3(kSortThreads);
     CK(cudaLaunchKernelEx(&cfg, k_sort_lsd_all, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, ctl, cap,
-                          ctx->force_lsd, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts, ctx->d_hint));
+                          ctx->force_lsd, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts, ctx->d_res));
     CK_LAUNCH();
     return ASTRE_OK;
 }
 
-int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
-{
-    if (!ctx) return ASTRE_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->hier_dirty) if (int rc = rebuild_levels(ctx)) return rc;
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    const uint32_t n = ctx->n_entities;
-    const bool cull = (stage_flags & ASTRE_FRAME_CULL) && ctx->views_per_world > 0;
-    const bool sort_now = cull && (stage_flags & ASTRE_FRAME_SORT);
-    const bool sort = cull && (stage_flags & (ASTRE_FRAME_SORT | ASTRE_FRAME_SORT_LATER));   // plan + digit histograms
-    const uint32_t n_counts = ctx->n_worlds * ctx->views_per_world;
-    if (ctx->n_worlds > 1 && (uint64_t)ctx->n_worlds * ctx->entities_per_world < n)
-        return fail(ctx, ASTRE_ERR_STATE, "entity count %u exceeds n_worlds*entities_per_world", n);
+namespace {
 
-    ctx->epoch = (ctx->epoch + 1) & ((1u << 27) - 1u);
-    if (ctx->epoch == 0) {   // tag wrapped: clear stale look-back words once
-        const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
-        CK(cudaMemsetAsync(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long), s));
-        ctx->epoch = 1;
-    }
-    CK(cudaEventRecord(ctx->ev_begin, s));
-    // digit plan of the sort from the key fields in use (all other key bits are zero in every key)
-    SortPlan plan;
-    BinPlan bp;
-    std::memset(&plan, 0, sizeof plan);
-    std::memset(&bp, 0, sizeof bp);
-    if (sort) {
-        auto bits_for = [](uint64_t max_value) { uint32_t b = 0; while (b < 32 && (max_value >> b)) ++b; return b; };
-        const uint32_t wb = ctx->world_bits;
-        const uint64_t local_max = (ctx->n_worlds > 1 ? ctx->entities_per_world : n) ? (uint64_t)(ctx->n_worlds > 1 ? ctx->entities_per_world : n) - 1 : 0;
-        unsigned long long live = (1ull << bits_for(local_max)) - 1ull;
-        live |= ((1ull << 14) - 1ull) << (26 - wb);
-        live |= ((1ull << bits_for(ctx->n_meshes ? ctx->n_meshes - 1 : 0)) - 1ull) << (40 - wb);
-        live |= (unsigned long long)ctx->shader_or << (51 - wb);
-        live |= ((1ull << bits_for(ctx->views_per_world ? ctx->views_per_world - 1 : 0)) - 1ull) << (59 - wb);
-        if (wb) live |= ((1ull << wb) - 1ull) << (64 - wb);
-        plan = make_sort_plan(live);
-        // buckets of ~4-8 keys: one bin per 8 keys of the last frame that finished (a hint -- any width sorts correctly;
-        // before the first frame: one key per 16 entity-view pairs)
-        const unsigned long long seen = *(volatile unsigned long long *)ctx->h_hint;
-        const unsigned long long expect = seen != ~0ull ? std::min<unsigned long long>(seen, ctx->max_keys)
-                                                        : (unsigned long long)n * ctx->views_per_world / 16ull;
-        uint32_t want = kMinBinBits;
-        while (want < ctx->cap_bin_bits && (1ull << want) * 8ull < expect) ++want;
-        if (ctx->bin_bits_override >= 0) want = std::min<uint32_t>((uint32_t)ctx->bin_bits_override, ctx->cap_bin_bits);
-        bp = make_bin_plan(live, want);
-    }
+// Every launch of one frame on stream s (also what a CUDA graph of the frame captures: no allocation, no
+// synchronisation, no event in here unless `timing`).
+int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool timing)
+{
+    const uint32_t stage_flags = fp.stage_flags, n = fp.n, n_counts = fp.n_counts;
+    const bool cull = fp.cull, sort_now = fp.sort_now;
+    const SortPlan &plan = fp.plan;
+    const BinPlan &bp = fp.bp;
     const uint32_t n_bins = bp.bits ? (1u << bp.bits) : 0u;
     k_frame_begin<<<std::max<uint32_t>(64u, std::min<uint32_t>(n_bins / 4096u, (uint32_t)ctx->sm_count * 4u)), 256, 0, s>>>(
-        ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->epoch, ctx->d_bins, n_bins);
+        ctx->d_ctl, ctx->d_sc, ctx->d_counts, n_counts, ctx->d_bins, n_bins);
     CK_LAUNCH();
 
     const FrameParams P = params_of(ctx, cull);
-    CK(cudaEventRecord(ctx->ev_cull0, s));
+    if (timing) CK(cudaEventRecord(ctx->ev_cull0, s));
     if (n) {
         const bool worlds = ctx->n_worlds > 1;
         const uint32_t fused_grid = (uint32_t)(ctx->sm_count * ctx->fused_blocks_per_sm);
@@ -854,10 +847,9 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             }
         }
     }
-    CK(cudaEventRecord(ctx->ev_cull1, s));
+    if (timing) CK(cudaEventRecord(ctx->ev_cull1, s));
 
     if (stage_flags & ASTRE_FRAME_BASIS) {
-        if (!ctx->d_basis) CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
         if (n) {
             float *b = ctx->d_basis;
             const size_t stride = (size_t)ctx->cap_entities * 3;
@@ -869,10 +861,6 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     const bool counts_in_sort = sort_now && bp.bits != 0;      // the sort's last launch also scans the counts
     if (sort_now) { if (int rc = launch_sort(ctx, bp, plan, n_counts, s)) return rc; }
-    ctx->sort_pending = sort && !sort_now;
-    ctx->pending_plan = plan;
-    ctx->pending_bins = bp;
-    ctx->last_sorted = sort_now && bp.bits != 0;
     if (n_counts && !counts_in_sort) {
         cudaLaunchAttribute pdl;
         pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -880,13 +868,119 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         cudaLaunchConfig_t cfg{};
         cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.gridDim = dim3(1); cfg.blockDim = dim3(256);
         CK(cudaLaunchKernelEx(&cfg, k_scan_counts, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts,
-                              (const FrameControl *)ctx->d_ctl, ctx->d_hint));
+                              (const FrameControl *)ctx->d_ctl, (const SortControl *)ctx->d_sc, ctx->d_res));
         CK_LAUNCH();
     }
+    return ASTRE_OK;
+}
+
+bool same_plan(const FramePlan &a, const FramePlan &b) { return std::memcmp(&a, &b, sizeof(FramePlan)) == 0; }
+
+}  // namespace
+
+int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->hier_dirty) if (int rc = rebuild_levels(ctx)) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const uint32_t n = ctx->n_entities;
+    FramePlan fp;
+    std::memset(&fp, 0, sizeof fp);                      // also the padding: plans are compared bytewise
+    fp.stage_flags = stage_flags & ~(uint32_t)ASTRE_FRAME_GRAPH;
+    fp.n = n;
+    fp.cull = (stage_flags & ASTRE_FRAME_CULL) && ctx->views_per_world > 0;
+    fp.sort_now = fp.cull && (stage_flags & ASTRE_FRAME_SORT);
+    fp.sort = fp.cull && (stage_flags & (ASTRE_FRAME_SORT | ASTRE_FRAME_SORT_LATER));   // bucket counts + plans
+    fp.n_counts = ctx->n_worlds * ctx->views_per_world;
+    if (ctx->n_worlds > 1 && (uint64_t)ctx->n_worlds * ctx->entities_per_world < n)
+        return fail(ctx, ASTRE_ERR_STATE, "entity count %u exceeds n_worlds*entities_per_world", n);
+
+    // The frame number that tags look-back words lives on the device (k_frame_begin bumps it, so a captured graph
+    // needs no per-frame parameter); this mirror advances in step and clears the tagged words when the tag wraps.
+    ctx->epoch = ctx->epoch + 1;
+    if (ctx->epoch >= kEpochWrap) {
+        const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
+        CK(cudaMemsetAsync(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(ctx->d_sc->scan_state, 0, sizeof(ctx->d_sc->scan_state), s));
+        ctx->epoch = 1;
+    }
+    // plans of the sort from the key fields in use (all other key bits are zero in every key)
+    if (fp.sort) {
+        auto bits_for = [](uint64_t max_value) { uint32_t b = 0; while (b < 32 && (max_value >> b)) ++b; return b; };
+        const uint32_t wb = ctx->world_bits;
+        const uint64_t local_max = (ctx->n_worlds > 1 ? ctx->entities_per_world : n) ? (uint64_t)(ctx->n_worlds > 1 ? ctx->entities_per_world : n) - 1 : 0;
+        unsigned long long live = (1ull << bits_for(local_max)) - 1ull;
+        live |= ((1ull << 14) - 1ull) << (26 - wb);
+        live |= ((1ull << bits_for(ctx->n_meshes ? ctx->n_meshes - 1 : 0)) - 1ull) << (40 - wb);
+        live |= (unsigned long long)ctx->shader_or << (51 - wb);
+        live |= ((1ull << bits_for(ctx->views_per_world ? ctx->views_per_world - 1 : 0)) - 1ull) << (59 - wb);
+        if (wb) live |= ((1ull << wb) - 1ull) << (64 - wb);
+        fp.plan = make_sort_plan(live);
+        // buckets of ~4-8 keys: one bin per 8 keys of the last frame that finished (a hint -- any width sorts correctly;
+        // before the first frame: one key per 16 entity-view pairs).  The width only follows the hint when it is off by
+        // more than one bit, so that steady frames keep their plan (and their captured graph).
+        const unsigned long long seen = *(volatile unsigned long long *)&ctx->h_res->key_total;
+        const unsigned long long expect = seen != ~0ull ? std::min<unsigned long long>(seen, ctx->max_keys)
+                                                        : (unsigned long long)n * ctx->views_per_world / 16ull;
+        uint32_t want = kMinBinBits;
+        while (want < ctx->cap_bin_bits && (1ull << want) * 8ull < expect) ++want;
+        if (ctx->last_want_bits && want + 1 >= ctx->last_want_bits && want <= ctx->last_want_bits + 1) want = ctx->last_want_bits;
+        ctx->last_want_bits = want;
+        if (ctx->bin_bits_override >= 0) want = std::max<uint32_t>(2u, std::min<uint32_t>((uint32_t)ctx->bin_bits_override, ctx->cap_bin_bits));
+        fp.bp = make_bin_plan(live, want);
+    }
+    if ((stage_flags & ASTRE_FRAME_BASIS) && !ctx->d_basis)
+        CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
+
+    CK(cudaEventRecord(ctx->ev_begin, s));
+    if (stage_flags & ASTRE_FRAME_GRAPH) {
+        // One cudaGraphLaunch instead of 6+ launches: what matters for small frames, where the launches ARE the frame.
+        // Captured when the plan, the views, the hierarchy or the stream changed (an exec update when the topology is the same).
+        const bool stale = !ctx->graph_exec || !same_plan(fp, ctx->graph_plan) || ctx->graph_views_version != ctx->views_version ||
+                           ctx->graph_levels_version != ctx->levels_version || ctx->graph_stream != s;
+        if (stale) {
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const uint64_t launches_before = ctx->launches;
+            const int rc = enqueue_frame(ctx, fp, s, false);
+            const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            ctx->graph_launches = (uint32_t)(ctx->launches - launches_before);
+            ctx->launches = launches_before;
+            if (rc != ASTRE_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(ctx, ASTRE_ERR_CUDA, "graph capture of the frame failed: %s", cudaGetErrorString(ce));
+            bool updated = false;
+            if (ctx->graph_exec) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess;
+                if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            }
+            if (!updated) {
+                const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+                if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; return fail(ctx, ASTRE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            }
+            cudaGraphDestroy(g);
+            ctx->graph_plan = fp;
+            ctx->graph_views_version = ctx->views_version;
+            ctx->graph_levels_version = ctx->levels_version;
+            ctx->graph_stream = s;
+            ++ctx->graph_captures;
+        }
+        CK(cudaGraphLaunch(ctx->graph_exec, s));
+        ctx->launches += ctx->graph_launches;
+        ctx->last_timed = false;
+    } else {
+        if (int rc = enqueue_frame(ctx, fp, s, true)) return rc;
+        ctx->last_timed = true;
+    }
     CK(cudaEventRecord(ctx->ev_end, s));
+    ctx->sort_pending = fp.sort && !fp.sort_now;
+    ctx->pending_plan = fp.plan;
+    ctx->pending_bins = fp.bp;
+    ctx->last_sorted = fp.sort_now && fp.bp.bits != 0;
     ctx->frame_done = true;
     ctx->results_cached = false;
-    ctx->last_flags = stage_flags;
+    ctx->last_flags = fp.stage_flags;
     ctx->last_stream = s;
     return ASTRE_OK;
 }
@@ -940,6 +1034,7 @@ int astre_gpu_last_cull_ms(astre_gpu_ctx *ctx, float *ms)
 {
     if (!ctx || !ms) return ASTRE_ERR_INVALID;
     if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
+    if (!ctx->last_timed) return fail(ctx, ASTRE_ERR_STATE, "the last frame was replayed from a CUDA graph (ASTRE_FRAME_GRAPH): no per-kernel events");
     CK(cudaEventSynchronize(ctx->ev_cull1));
     CK(cudaEventElapsedTime(ms, ctx->ev_cull0, ctx->ev_cull1));
     return ASTRE_OK;
@@ -1021,8 +1116,7 @@ int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path)
     if (!ctx->frame_done) return fail(ctx, ASTRE_ERR_STATE, "no frame has been run");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->last_stream));
-    *path = 0;
-    if (ctx->last_sorted) CK(cudaMemcpy(path, &ctx->d_sc->path, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    *path = ctx->last_sorted ? ctx->h_res->path : 0u;
     return ASTRE_OK;
 }
 
@@ -1135,6 +1229,35 @@ int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_
     CK_LAUNCH();
     CK(cudaMemcpyAsync(out, ctx->d_gather, n * 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_draw_list(astre_gpu_ctx *ctx, uint64_t *keys, float *world16, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = cache_results(ctx)) return rc;                     // one synchronisation: the frame has finished
+    if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
+    const uint64_t have = std::min<uint64_t>(ctx->h_total, ctx->max_keys);
+    *n_out = have;
+    const uint64_t n = std::min(have, cap);
+    if (!n) return ASTRE_OK;
+    cudaStream_t s = ctx->last_stream;
+    if (world16) {
+        if (ctx->cap_gather < n) {
+            if (ctx->d_gather) CK(cudaFree(ctx->d_gather));
+            ctx->d_gather = nullptr;
+            CK(cudaMalloc(&ctx->d_gather, n * 64));
+            ctx->cap_gather = n;
+        }
+        const uint32_t grid = std::min<uint32_t>(ceil_div(n * 4, 256), (uint32_t)ctx->sm_count * 8);
+        k_gather_world<<<grid, 256, 0, s>>>(ctx->d_keys[ctx->h_result_buf], 0ull, n, ctx->d_world, ctx->d_gather,
+                                            ctx->world_bits, ctx->entities_per_world);
+        CK_LAUNCH();
+    }
+    if (keys) CK(cudaMemcpyAsync(keys, ctx->d_keys[ctx->h_result_buf], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (world16) CK(cudaMemcpyAsync(world16, ctx->d_gather, n * 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));                                   // and one for both copies
     return ASTRE_OK;
 }
 

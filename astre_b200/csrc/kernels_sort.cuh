@@ -195,16 +195,50 @@ __device__ __forceinline__ void scan_counts_block(const uint32_t *__restrict__ c
     __syncthreads();
 }
 
+// What the host wants to know about a finished frame, mirrored into MAPPED HOST memory by the frame's last launch:
+// reading a frame's results then costs one stream synchronisation and no copy (small frames are all latency).
+// key_total doubles as the hint that sizes the next frame's buckets.
+constexpr uint32_t kInlineCounts = 256;
+struct FrameResultHost {
+    unsigned long long key_total;
+    uint32_t overflow, result_buf, path;
+    uint32_t n_counts;                                  // counts / offsets mirrored below (0: too many, copy them from the device)
+    uint32_t counts[kInlineCounts];
+    unsigned long long offsets[kInlineCounts + 1];
+};
+
+// by one block of 256 threads, after scan_counts_block
+__device__ __forceinline__ void publish_results(FrameResultHost *res, const FrameControl *ctl, const SortControl *sc,
+                                                const uint32_t *__restrict__ counts, const unsigned long long *__restrict__ offsets,
+                                                const uint32_t n_counts, const bool with_counts)
+{
+    if (!res) return;
+    if (threadIdx.x == 0) {
+        res->key_total = ctl->key_total;
+        res->overflow = ctl->overflow;
+        res->result_buf = sc->result_buf;
+        res->path = sc->path;
+    }
+    if (with_counts) {
+        const bool inl = n_counts <= kInlineCounts;
+        if (threadIdx.x == 0) res->n_counts = inl ? n_counts : 0u;
+        if (inl) {
+            if (threadIdx.x < n_counts) res->counts[threadIdx.x] = counts[threadIdx.x];
+            for (uint32_t i = threadIdx.x; i <= n_counts; i += 256u) res->offsets[i] = offsets[i];
+        }
+    }
+}
+
 // Frames that do not sort in the same call: the scan of the per-view counts as its own launch
-// (sorted frames get it from block 0 of k_sort_lsd_all).  Also leaves the key total in `hint`.
+// (sorted frames get it from block 0 of k_sort_lsd_all).
 __global__ void __launch_bounds__(256)
 k_scan_counts(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n,
-              const FrameControl *ctl, unsigned long long *hint)
+              const FrameControl *ctl, const SortControl *sc, FrameResultHost *res)
 {
     __shared__ unsigned long long s_warp[8];
     cudaGridDependencySynchronize();
-    if (threadIdx.x == 0 && hint) *hint = ctl->key_total;
     scan_counts_block(counts, offsets, n, s_warp);
+    publish_results(res, ctl, sc, counts, offsets, n, true);
 }
 
 // ---- bucket sort ------------------------------------------------------------------------------------------
@@ -336,16 +370,13 @@ k_bin_scatter(const unsigned long long *__restrict__ in, unsigned long long *__r
 __global__ void __launch_bounds__(256)
 k_bin_rank(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out, const uint32_t *__restrict__ cursor,
            const uint32_t *__restrict__ chunk_first, const __grid_constant__ BinPlan bp, SortControl *sc,
-           const FrameControl *ctl, const unsigned long long cap, const uint32_t force_lsd, unsigned long long *hint)
+           const FrameControl *ctl, const unsigned long long cap, const uint32_t force_lsd)
 {
     __shared__ unsigned long long s_keys[kRankSmemKeys];
     cudaGridDependencySynchronize();
     const uint32_t n = sort_key_count(ctl, cap);
     if (sort_takes_fallback(sc, n, force_lsd)) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        sc->result_buf = 0u; sc->path = kSortBins; sc->n_keys = n;
-        if (hint) *hint = ctl->key_total;      // mapped host word (next frame's bucket count); the PCIe write overlaps the ranking
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->result_buf = 0u; sc->path = kSortBins; sc->n_keys = n; }
     const uint32_t n_chunks = n / kChunkKeys + 1u;                    // chunk c exists while 1024 c <= n
     for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const uint32_t d0 = chunk_first[c];
@@ -437,7 +468,7 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
                unsigned long long *__restrict__ lookback, const __grid_constant__ SortPlan plan, const FrameControl *ctl,
                const unsigned long long cap, const uint32_t force_lsd,
                const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n_counts,
-               unsigned long long *hint)
+               FrameResultHost *res)
 {
     constexpr int THREADS = kSortThreads, ITEMS = 8;
     constexpr int kTile = THREADS * ITEMS;
@@ -450,8 +481,10 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
     const uint32_t n = sort_key_count(ctl, cap);
     // the frame's last launch: block 0 also scans the per-(world, view) counts into list offsets
     if (blockIdx.x == 0 && n_counts) scan_counts_block(counts, offsets, n_counts, s_keys);
-    if (!sort_takes_fallback(sc, n, force_lsd)) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && hint) *hint = ctl->key_total;
+    if (!sort_takes_fallback(sc, n, force_lsd)) {
+        if (blockIdx.x == 0) publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0);   // the bucket sort ran
+        return;
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -620,7 +653,11 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
         }
         sort_grid_barrier(&sc->lsd_barrier, ++round * gridDim.x);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { sc->result_buf = executed & 1u; sc->path = kSortLsd; }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) { sc->result_buf = executed & 1u; sc->path = kSortLsd; }
+        __syncthreads();
+        publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0);
+    }
 }
 
 }  // namespace astre

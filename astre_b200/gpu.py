@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import AstreError, DrawRun, MeshBounds, load_library
 
-FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER = 1, 2, 4, 8, 16
+FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER, FRAME_GRAPH = 1, 2, 4, 8, 16, 32
 FRAME_ALL = 7
 
 PHASE_OPAQUE, PHASE_TRANSPARENT, PHASE_SHADOW_CASTER, PHASE_DEBUG = 1, 2, 4, 8
@@ -211,6 +211,14 @@ class GpuContext:
         out = np.empty((n, 16), np.float32) if out is None else out
         self._check(self._lib.astre_gpu_read_visible_world(self._h, int(first_key), int(n), _ptr(out, C.c_float)))
         return out
+
+    def read_draw_list(self, keys_out, world_out):
+        """Sorted keys and the world matrices of their entities in list order, into caller buffers (uint64 [cap], float32
+        [cap, 16]); returns the list length.  One synchronisation for the frame, one for both copies."""
+        n = C.c_uint64()
+        cap = min(len(keys_out), len(world_out))
+        self._check(self._lib.astre_gpu_read_draw_list(self._h, _ptr(keys_out, C.c_uint64), _ptr(world_out, C.c_float), cap, C.byref(n)))
+        return int(n.value)
 
     def read_runs(self):
         """Draw runs of the sorted list: array [n, 4] = first, count, world<<5|view, shader<<11|mesh."""

@@ -274,7 +274,7 @@ def run_reference(args):
 class Bench:
     """One workload on this rank's GPU: device-resident timing, dominant-kernel timing, end to end, parity."""
 
-    def __init__(self, name, rank, local_rank, world, torch, dist):
+    def __init__(self, name, rank, local_rank, world, torch, dist, use_graph=True):
         from astre_b200 import GpuContext, gpu, multi, scenes
         self.torch, self.dist, self.gpu, self.multi = torch, dist, gpu, multi
         self.name, self.rank, self.world = name, rank, world
@@ -291,6 +291,8 @@ class Bench:
         self.ctx.set_stream(self.stream.cuda_stream)
         self.rank_major = s.n_worlds > 1          # whole-world shards: the global list is the concatenation of the ranks' lists
         self.exchange = multi.CountExchange(self.ctx, self.n_counts, rank_major=self.rank_major) if world > 1 and name != "config1" else None
+        # single-GPU steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
+        self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph and self.exchange is None else 0)
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -304,7 +306,7 @@ class Bench:
     def step(self):
         g = self.gpu
         if self.exchange is None:
-            self.ctx.frame(g.FRAME_ALL)
+            self.ctx.frame(self.frame_flags)
             return
         # counts are final when the cull kernel ends: stage them, hand the exchange to the side stream, sort
         self.ctx.frame(g.FRAME_TRANSFORM | g.FRAME_CULL | g.FRAME_SORT_LATER)
@@ -385,20 +387,18 @@ class Bench:
 
         def read_results():
             ctx.read_counts(cnt_np)
-            k = ctx.read_all_keys(keys_np)
-            ctx.read_visible_world(0, len(k), vis_np)
-            return len(k)
+            return ctx.read_draw_list(keys_np, vis_np)       # sorted keys + the visible entities' world matrices
 
         def all_dirty():
             ctx.update_trs_range(0, n, pos_np, rot_np, scl_np)
-            ctx.frame(g.FRAME_ALL)
+            ctx.frame(self.frame_flags)
             return read_results()
 
         ms, nk = timed(all_dirty, steps)
         out = {"value": self.total_entities / (ms * 1e-3), "unit": "entities/s", "ms_per_step": ms,
                "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(self.n_counts * 4 + nk * 8 + nk * 64),
-               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_frame + read_counts + "
-                       "read_all_keys + read_visible_world"}
+               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_frame + astre_gpu_read_counts + "
+                       "astre_gpu_read_draw_list (sorted keys + world matrices of the visible entities)"}
         # the case the mirror was built for: a dirty subset pushed as a slot list (astre_gpu_update_trs)
         rng = np.random.default_rng(7)
         for pct in (1, 10):
@@ -409,7 +409,7 @@ class Bench:
 
             def dirty():
                 ctx.update_trs(sl_h, p_h, r_h, s_h)
-                ctx.frame(g.FRAME_ALL)
+                ctx.frame(self.frame_flags)
                 return read_results()
 
             ms_d, nk_d = timed(dirty, steps)
@@ -453,13 +453,14 @@ class Bench:
 
 
 def run_workload(name, rank, local_rank, world, args, torch, dist, steps, warmup, e2e_steps, cpu_reps, headline):
-    b = Bench(name, rank, local_rank, world, torch, dist)
+    b = Bench(name, rank, local_rank, world, torch, dist, use_graph=not args.no_graph)
     try:
         ms_step, launches = b.device_resident(steps, warmup)
         kernel_ms = b.kernel_timing(min(steps, 20))
         out = {"workload": b.workload, "scaling": b.scaling, "value": b.total_entities / (ms_step * 1e-3), "unit": "entities/s",
                "ms_per_step": ms_step, "entities_per_gpu": b.n, "views": b.F, "visible_keys_rank0": int(b.total_keys),
                "sort_path": {0: "none", 1: "bucket", 2: "lsd-fallback"}[b.sort_path], "gpu_launches": launches,
+               "frame_as_cuda_graph": bool(b.frame_flags & b.gpu.FRAME_GRAPH),
                "roofline": b.roofline(kernel_ms, ms_step), "e2e": b.end_to_end(e2e_steps)}
         parity, cpu = b.parity_and_cpu(cpu_reps, not args.no_cpu_baseline)
         out["parity"], out["cpu_baseline"] = parity, cpu
@@ -482,6 +483,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip config.extra_workloads")
     ap.add_argument("--entities", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the frame kernel by kernel instead of replaying one CUDA graph")
     args = ap.parse_args()
     if args.entities:
         globals()["N_PER_GPU"] = args.entities

@@ -72,6 +72,9 @@ enum {
     ASTRE_FRAME_SORT      = 1u << 2,  /* device sort of the emitted keys                     */
     ASTRE_FRAME_BASIS     = 1u << 3,  /* forward/up/right of every entity                    */
     ASTRE_FRAME_SORT_LATER = 1u << 4, /* prepare the sort (bucket counts) but run it in astre_gpu_sort */
+    ASTRE_FRAME_GRAPH     = 1u << 5,  /* replay the frame's launches as ONE CUDA graph (captured again when the   */
+                                      /* plan, views, hierarchy or stream change); astre_gpu_last_cull_ms is then  */
+                                      /* unavailable.  For small frames, where launch latency is the frame.        */
     ASTRE_FRAME_ALL       = 7u
 };
 
@@ -215,6 +218,11 @@ ASTRE_API int astre_gpu_read_all_keys(astre_gpu_ctx *ctx, uint64_t *keys, uint64
 /* World matrices of the first n keys of the sorted list, in list order (what
  * VisualSystem copies into RenderProxy.inputs["uModel"], visual_system.cpp:47). */
 ASTRE_API int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_t n, float *mat4_colmajor);
+/* The whole draw list in one call -- sorted keys and, in the same order, the world matrices of their entities
+ * (what VisualSystem::run leaves in frame.render_proxies[e].inputs.in_mat4["uModel"], visual_system.cpp:47):
+ * one synchronisation for the frame and one for both copies.  keys / mat4_colmajor may be NULL; at most cap
+ * entries are written, *n_out is the list's length. */
+ASTRE_API int astre_gpu_read_draw_list(astre_gpu_ctx *ctx, uint64_t *keys, float *mat4_colmajor, uint64_t cap, uint64_t *n_out);
 /* f2: the sorted list of the last frame cut into draw runs -- maximal stretches of keys with the
  * same (world, view, shader, mesh), i.e. what one instanced / indirect draw covers instead of one
  * IRenderer::render per proxy (Pipeline/src/deferred_shading.cpp:115-132, Render/src/opengl/opengl.cpp:563-670).
