@@ -132,6 +132,11 @@ struct astre_gpu_ctx {
     std::vector<Level> levels;
     uint32_t *d_level_slots = nullptr;
     size_t cap_level_slots = 0;
+    // breadth-first forests: per-CTA descendant ranges ("cones", k_hier_cones)
+    uint2 *d_cones = nullptr;
+    size_t cap_cones = 0;
+    uint32_t n_cones = 0;                // 0: the hierarchy is not breadth-first ordered (or ASTRE_NO_CONES): per-level launches
+    bool use_cones = true;
 
     std::vector<uint64_t> h_entity_id;
 
@@ -151,6 +156,7 @@ struct astre_gpu_ctx {
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     int fused_blocks_per_sm = 2;
+    int cone_blocks_per_sm = 2;
     bool coop_launch = false;        // device supports cooperative launches (multi-level hierarchy launches)
     bool use_pdl = true;             // programmatic dependent launch for the sort chain (ASTRE_NO_PDL disables)
     uint32_t small_level = 32768;    // hierarchy levels below this many entities take the thread-per-entity kernel (measured: config 2, 0.159 -> 0.139 ms)
@@ -302,6 +308,64 @@ int rebuild_levels(astre_gpu_ctx *ctx)
         L.contiguous = (order[start[l + 1] - 1] - L.first + 1 == L.count);
         L.list_offset = start[l];
         any_list |= !L.contiguous;
+    }
+    // Cones: every level a contiguous range in slot order and parents non-decreasing along each level => the
+    // descendants of a run of roots are one contiguous range per level.
+    ctx->n_cones = 0;
+    if (ctx->use_cones && !any_list && n_levels > 1 && n_levels <= 64) {
+        bool bfs = true;
+        for (int l = 1; l < n_levels && bfs; ++l) {
+            const Level &L = ctx->levels[l], &U = ctx->levels[l - 1];
+            uint32_t prev = 0;
+            for (uint32_t i = 0; i < L.count; ++i) {
+                const uint32_t p = ctx->h_parent[L.first + i];
+                if (p < U.first || p >= U.first + U.count || p < prev) { bfs = false; break; }
+                prev = p;
+            }
+        }
+        if (bfs) {
+            // descendants per root, bottom-up
+            std::vector<uint32_t> sub(n, 1u);
+            for (int l = n_levels - 1; l >= 1; --l) {
+                const Level &L = ctx->levels[l];
+                for (uint32_t i = 0; i < L.count; ++i) sub[ctx->h_parent[L.first + i]] += sub[L.first + i];
+            }
+            const Level &R = ctx->levels[0];
+            const uint32_t want = std::min<uint32_t>((uint32_t)(ctx->sm_count * ctx->cone_blocks_per_sm), std::max<uint32_t>(R.count, 1u));
+            // cut the roots into `want` runs of about n / want entities each
+            std::vector<uint32_t> cut(want + 1, R.first + R.count);
+            {
+                uint64_t acc = 0;
+                uint32_t c = 0;
+                cut[0] = R.first;
+                for (uint32_t i = 0; i < R.count && c + 1 < want; ++i) {
+                    acc += sub[R.first + i];
+                    if (acc * want >= (uint64_t)n * (c + 1)) cut[++c] = R.first + i + 1;
+                }
+                for (uint32_t k = c + 1; k <= want; ++k) cut[k] = R.first + R.count;
+            }
+            std::vector<uint2> ranges((size_t)want * n_levels);
+            for (uint32_t c = 0; c < want; ++c) ranges[(size_t)c * n_levels] = make_uint2(cut[c], cut[c + 1]);
+            for (int l = 1; l < n_levels; ++l) {
+                const Level &L = ctx->levels[l];
+                const uint32_t *par = ctx->h_parent.data() + L.first;
+                for (uint32_t c = 0; c < want; ++c) {
+                    const uint2 up = ranges[(size_t)c * n_levels + l - 1];         // parents of this cone on the level above
+                    const uint32_t lo = (uint32_t)(std::lower_bound(par, par + L.count, up.x) - par);
+                    const uint32_t hi = (uint32_t)(std::lower_bound(par, par + L.count, up.y) - par);
+                    ranges[(size_t)c * n_levels + l] = up.x < up.y ? make_uint2(L.first + lo, L.first + hi) : make_uint2(L.first, L.first);
+                }
+            }
+            if (ctx->cap_cones < ranges.size()) {
+                if (ctx->d_cones) cudaFree(ctx->d_cones);
+                ctx->d_cones = nullptr;
+                CK(cudaMalloc(&ctx->d_cones, ranges.size() * sizeof(uint2)));
+                ctx->cap_cones = ranges.size();
+            }
+            CK(cudaMemcpyAsync(ctx->d_cones, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->n_cones = want;
+        }
     }
     if (any_list) {
         if (ctx->cap_level_slots < n) {
@@ -479,6 +543,11 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
         CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         ctx->coop_launch = coop != 0 && !std::getenv("ASTRE_NO_COOP");
         if (const char *m = std::getenv("ASTRE_SMALL_LEVEL")) ctx->small_level = (uint32_t)std::atol(m);
+        if (std::getenv("ASTRE_NO_CONES")) ctx->use_cones = false;
+        int occ_cones = 0;
+        CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cones, k_hier_cones<true>, kBlockThreads, 0));
+        ctx->cone_blocks_per_sm = std::max(occ_cones, 1);
+        if (const char *m = std::getenv("ASTRE_CONES_PER_SM")) ctx->cone_blocks_per_sm = std::max(std::atoi(m), 1);
         if (std::getenv("ASTRE_NO_PDL")) ctx->use_pdl = false;
     }
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
@@ -495,7 +564,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
-                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_bins, ctx->d_chunk_first, ctx->d_heads,
+                     ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_cones, ctx->d_bins, ctx->d_chunk_first, ctx->d_heads,
                      ctx->d_head_counts,
                      ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
@@ -811,7 +880,18 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
             barrier_rounds += (LT.n - 1) * g;
             claim_sets += LT.n * std::min<uint32_t>(ctx->claim_groups, g);
         };
-        if (!ctx->has_parents) {
+        if (ctx->has_parents && ctx->n_cones) {
+            // breadth-first forest: one launch, a CTA per cone, levels separated by __syncthreads()
+            const uint32_t n_levels = (uint32_t)ctx->levels.size();
+            cudaLaunchAttribute pdl;
+            pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(ctx->n_cones); cfg.blockDim = dim3(kBlockThreads); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+            if (cull) CK(cudaLaunchKernelEx(&cfg, k_hier_cones<true>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
+            else CK(cudaLaunchKernelEx(&cfg, k_hier_cones<false>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
+            CK_LAUNCH();
+        } else if (!ctx->has_parents) {
             LevelTable LT{};
             LT.n = 1; LT.first[0] = 0; LT.end[0] = n;
             launch_ranges(LT, false);

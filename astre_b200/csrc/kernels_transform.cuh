@@ -410,4 +410,84 @@ k_transform_cull_indexed(const FrameParams P, const __grid_constant__ BinPlan bp
     }
 }
 
+// ---------------------------------------------------------------------------
+// Hierarchies stored in breadth-first order (every level a contiguous slot range, parents non-decreasing along a
+// level -- what a level-sorted loader produces, and what configuration 2 is): the descendants of a contiguous run of
+// roots are ONE contiguous range per level, a "cone".  The host cuts the forest into cones of equal size; a CTA
+// walks its cone level by level, so parent-before-child becomes a __syncthreads() instead of a grid-wide barrier or
+// a launch boundary, and a level costs two dependent L2 round trips instead of ~15 us.  Parent rows were written by
+// this CTA a level earlier and are read back through L2 (ld.global.cg).  One entity per thread, warp-aggregated
+// compaction, per-view counts in shared memory (one global atomic per view and CTA).
+// ---------------------------------------------------------------------------
+template <bool CULL>
+__global__ void __launch_bounds__(kBlockThreads, 2)
+k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint2 *__restrict__ ranges, const uint32_t n_levels)
+{
+    __shared__ float4 s_scratch[kBlockThreads * 4];
+    __shared__ uint32_t s_counts[32];
+    const int lane = threadIdx.x & 31;
+    const uint32_t F = CULL ? P.views_per_world : 0u;
+    const bool one_world = P.n_worlds <= 1;
+    if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
+    cudaGridDependencySynchronize();
+    __syncthreads();
+    for (uint32_t level = 0; level < n_levels; ++level) {
+        const uint2 r = __ldg(ranges + (size_t)blockIdx.x * n_levels + level);
+        const uint32_t first = r.x, n = r.y - r.x;
+        const uint32_t n_round = (n + 31u) & ~31u;
+        for (uint32_t i = threadIdx.x; i < n_round; i += kBlockThreads) {
+            const bool active = i < n;
+            const uint32_t slot = active ? first + i : first;
+            const float *t = P.tiles + tile_index(slot, 0);
+            float m[16];
+            trs_matrix(t[PX * kWarpTile], t[PY * kWarpTile], t[PZ * kWarpTile],
+                       t[QX * kWarpTile], t[QY * kWarpTile], t[QZ * kWarpTile], t[QW * kWarpTile],
+                       t[SX * kWarpTile], t[SY * kWarpTile], t[SZ * kWarpTile], m, s_scratch + threadIdx.x * 4);
+            const uint32_t par = __float_as_uint(t[PARENT * kWarpTile]);
+            if (active && par != kNoParent) {
+                const float4 *pw = P.world + (size_t)par * 4;
+                const float4 a0 = __ldcg(pw), a1 = __ldcg(pw + 1), a2 = __ldcg(pw + 2), a3 = __ldcg(pw + 3);
+                const float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                                     a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+                float w[16];
+                mat4_mul(a, m, w);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) m[k] = w[k];
+            }
+            if (active) {
+                float4 *out = P.world + (size_t)slot * 4;
+                out[0] = make_float4(m[0], m[1], m[2], m[3]);
+                out[1] = make_float4(m[4], m[5], m[6], m[7]);
+                out[2] = make_float4(m[8], m[9], m[10], m[11]);
+                out[3] = make_float4(m[12], m[13], m[14], m[15]);
+            }
+            if (!CULL) continue;
+            const uint32_t world = one_world ? 0u : slot / P.entities_per_world;
+            uint32_t meta[1] = { __float_as_uint(t[META * kWarpTile]) }, vis[1] = { 0 }, phases[1], local[1];
+            local[0] = slot - world * P.entities_per_world;
+            const uint32_t flags = (meta[0] >> 19) & 31u, mesh = meta[0] & 2047u;
+            const bool cand = active && (flags & 1u) && mesh < P.n_meshes;
+            phases[0] = cand ? (flags >> 1) : 0u;
+            WorldBounds wb[1];
+            wb[0] = world_bounds(m, P.bounds[cand ? mesh : 0u]);
+            const GlobalViews V{ P.views + (size_t)world * F };
+            cull_views<1>(V, F, wb, phases, vis);
+            const uint32_t cnt = __popc(vis[0]);
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&P.ctl->key_total, (unsigned long long)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (!one_world)
+                    for (uint32_t v = 0; v < F; ++v)
+                        if ((vis[0] >> v) & 1u) atomicAdd(&P.counts[(size_t)world * F + v], 1u);
+                if (cnt) emit_keys<1>(P, bp, V, world, wb, vis, meta, local, base + (incl - cnt), one_world ? s_counts : nullptr);
+            }
+        }
+        __syncthreads();     // the next level reads this level's matrices (same CTA: block-scope ordering is enough)
+    }
+    if (CULL && one_world && threadIdx.x < F && s_counts[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
+}
+
 }  // namespace astre

@@ -51,6 +51,46 @@ def test_config2_hierarchy_1m(oracle):
     assert check_scene(oracle, scenes.config2()) > 0
 
 
+def _bfs_forest(rng, n_roots, n_levels, n_total):
+    """Random forest in breadth-first slot order: levels are contiguous, parents non-decreasing along a level, with
+    childless nodes and uneven branching (the shape the cone kernel takes)."""
+    sizes = [n_roots]
+    rest = n_total - n_roots
+    for l in range(1, n_levels):
+        take = rest if l == n_levels - 1 else int(rest * rng.uniform(0.2, 0.6))
+        sizes.append(max(take, 1))
+        rest -= sizes[-1]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    parent = np.full(starts[-1], gpu.NO_PARENT, np.uint32)
+    for l in range(1, n_levels):
+        up = np.sort(rng.integers(0, sizes[l - 1], sizes[l]))          # some parents get many children, some none
+        parent[starts[l]:starts[l + 1]] = (starts[l - 1] + up).astype(np.uint32)
+    return parent
+
+
+@pytest.mark.parametrize("cones", ["on", "off"])
+def test_hierarchy_breadth_first_forests(oracle, cones, monkeypatch):
+    """Breadth-first forests take k_hier_cones (a CTA per run of root subtrees); ASTRE_NO_CONES=1 takes the per-level
+    launches.  Both must equal the oracle."""
+    if cones == "off":
+        monkeypatch.setenv("ASTRE_NO_CONES", "1")
+    else:
+        monkeypatch.delenv("ASTRE_NO_CONES", raising=False)
+    rng = np.random.default_rng(41)
+    for n_roots, n_levels, n_total in ((1, 2, 40), (3, 5, 700), (500, 4, 60_000), (4000, 9, 300_000), (100_000, 3, 250_000)):
+        parent = _bfs_forest(rng, n_roots, n_levels, n_total)
+        s = scenes.config2(len(parent), levels=2)
+        s.parent = parent
+        s.pos = (s.pos * np.float32(0.3)).astype(np.float32)
+        check_scene(oracle, s)
+        with GpuContext(s.n, max_views=1) as ctx:                        # transform only, and frames repeat
+            scenes.load_into(ctx, s)
+            ctx.frame(gpu.FRAME_TRANSFORM)
+            ctx.frame(gpu.FRAME_TRANSFORM)
+            o_world, _ = oracle.transform_hierarchy(s.pos, s.rot, s.scale, s.parent)
+            assert np.array_equal(oracle_lib.bits(ctx.read_world(0, s.n)), oracle_lib.bits(o_world))
+
+
 def test_hierarchy_arbitrary_slot_order(oracle):
     """Levels that are not contiguous slot ranges take the indexed kernel."""
     s = scenes.config2(n=20_000)
