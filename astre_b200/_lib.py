@@ -47,6 +47,8 @@ SIGNATURES = {
     "astre_gpu_frame": (C.c_int, [_P, C.c_uint32, _P]),
     "astre_gpu_sort": (C.c_int, [_P, _P]),
     "astre_gpu_last_sort_path": (C.c_int, [_P, _U32]),
+    "astre_gpu_set_counts_mirror": (C.c_int, [_P, _P, _P]),
+    "astre_gpu_frame_index": (C.c_int, [_P, _U64]),
     "astre_gpu_global_offsets_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "astre_gpu_sync": (C.c_int, [_P]),
     "astre_gpu_set_stream": (C.c_int, [_P, _P]),

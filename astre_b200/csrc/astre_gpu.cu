@@ -76,6 +76,7 @@ struct astre_gpu_ctx {
     uint32_t *d_bins = nullptr;           // key sort: bucket counts -> bucket starts -> bucket ends (kernels_sort.cuh)
     uint32_t cap_bin_bits = 0;            // log2 of the bins allocated
     uint32_t *d_chunk_first = nullptr;    // key sort: first bucket of every 1024-key chunk
+    CountsMirror counts_mirror{{nullptr, nullptr}};   // astre_gpu_set_counts_mirror
     FrameResultHost *h_res = nullptr;     // mapped host block the frame's last launch writes: key total (also the hint that sizes
     FrameResultHost *d_res = nullptr;     // the next frame's buckets), sort outcome, counts and offsets -- read after one sync, no copy
     uint32_t force_lsd = 0;               // ASTRE_SORT_FORCE_LSD=1: always take the LSD fallback (tests)
@@ -825,7 +826,7 @@ static int launch_sort(astre_gpu_ctx *ctx, const BinPlan &bp, const SortPlan &pl
     CK_LAUNCH();
     cfg.gridDim = dim3((unsigned)ctx->sort_grid); cfg.blockDim = dim3(kSortThreads);
     CK(cudaLaunchKernelEx(&cfg, k_sort_lsd_all, ctx->d_keys[0], ctx->d_keys[1], ctx->d_sc, ctx->d_lookback, plan, ctl, cap,
-                          ctx->force_lsd, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts, ctx->d_res));
+                          ctx->force_lsd, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts, ctx->d_res, ctx->counts_mirror));
     CK_LAUNCH();
     return ASTRE_OK;
 }
@@ -948,7 +949,7 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
         cudaLaunchConfig_t cfg{};
         cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.gridDim = dim3(1); cfg.blockDim = dim3(256);
         CK(cudaLaunchKernelEx(&cfg, k_scan_counts, (const uint32_t *)ctx->d_counts, ctx->d_offsets, n_counts,
-                              (const FrameControl *)ctx->d_ctl, (const SortControl *)ctx->d_sc, ctx->d_res));
+                              (const FrameControl *)ctx->d_ctl, (const SortControl *)ctx->d_sc, ctx->d_res, ctx->counts_mirror));
         CK_LAUNCH();
     }
     return ASTRE_OK;
@@ -1187,6 +1188,23 @@ int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, 
         runs[i].world_view = (uint32_t)(heads[i].cls >> 19);
         runs[i].shader_mesh = (uint32_t)(heads[i].cls & ((1ull << 19) - 1ull));
     }
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_counts_mirror(astre_gpu_ctx *ctx, void *dev_slot0, void *dev_slot1)
+{
+    if (!ctx || (!dev_slot0) != (!dev_slot1)) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "pass two device buffers, or two NULLs to switch the mirror off") : ASTRE_ERR_INVALID;
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    ctx->counts_mirror.slot[0] = static_cast<uint32_t *>(dev_slot0);
+    ctx->counts_mirror.slot[1] = static_cast<uint32_t *>(dev_slot1);
+    ++ctx->views_version;              // kernel parameters of a captured frame graph
+    return ASTRE_OK;
+}
+
+int astre_gpu_frame_index(const astre_gpu_ctx *ctx, uint64_t *index)
+{
+    if (!ctx || !index) return ASTRE_ERR_INVALID;
+    *index = ctx->epoch;
     return ASTRE_OK;
 }
 

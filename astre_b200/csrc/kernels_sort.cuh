@@ -207,11 +207,19 @@ struct FrameResultHost {
     unsigned long long offsets[kInlineCounts + 1];
 };
 
+// Optional device-side copy of the per-view counts, alternating between two caller buffers by frame parity: what a
+// multi-GPU exchange reads while the NEXT frame (which zeroes the live counters) is already running.
+struct CountsMirror { uint32_t *slot[2]; };
+
 // by one block of 256 threads, after scan_counts_block
 __device__ __forceinline__ void publish_results(FrameResultHost *res, const FrameControl *ctl, const SortControl *sc,
                                                 const uint32_t *__restrict__ counts, const unsigned long long *__restrict__ offsets,
-                                                const uint32_t n_counts, const bool with_counts)
+                                                const uint32_t n_counts, const bool with_counts, const CountsMirror &mirror)
 {
+    if (with_counts && mirror.slot[0]) {
+        uint32_t *dst = mirror.slot[sc->epoch & 1u];
+        for (uint32_t i = threadIdx.x; i < n_counts; i += 256u) dst[i] = counts[i];
+    }
     if (!res) return;
     if (threadIdx.x == 0) {
         res->key_total = ctl->key_total;
@@ -233,12 +241,12 @@ __device__ __forceinline__ void publish_results(FrameResultHost *res, const Fram
 // (sorted frames get it from block 0 of k_sort_lsd_all).
 __global__ void __launch_bounds__(256)
 k_scan_counts(const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n,
-              const FrameControl *ctl, const SortControl *sc, FrameResultHost *res)
+              const FrameControl *ctl, const SortControl *sc, FrameResultHost *res, const CountsMirror mirror)
 {
     __shared__ unsigned long long s_warp[8];
     cudaGridDependencySynchronize();
     scan_counts_block(counts, offsets, n, s_warp);
-    publish_results(res, ctl, sc, counts, offsets, n, true);
+    publish_results(res, ctl, sc, counts, offsets, n, true, mirror);
 }
 
 // ---- bucket sort ------------------------------------------------------------------------------------------
@@ -468,7 +476,7 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
                unsigned long long *__restrict__ lookback, const __grid_constant__ SortPlan plan, const FrameControl *ctl,
                const unsigned long long cap, const uint32_t force_lsd,
                const uint32_t *__restrict__ counts, unsigned long long *__restrict__ offsets, const uint32_t n_counts,
-               FrameResultHost *res)
+               FrameResultHost *res, const CountsMirror mirror)
 {
     constexpr int THREADS = kSortThreads, ITEMS = 8;
     constexpr int kTile = THREADS * ITEMS;
@@ -482,7 +490,7 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
     // the frame's last launch: block 0 also scans the per-(world, view) counts into list offsets
     if (blockIdx.x == 0 && n_counts) scan_counts_block(counts, offsets, n_counts, s_keys);
     if (!sort_takes_fallback(sc, n, force_lsd)) {
-        if (blockIdx.x == 0) publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0);   // the bucket sort ran
+        if (blockIdx.x == 0) publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0, mirror);   // the bucket sort ran
         return;
     }
 
@@ -656,7 +664,7 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) { sc->result_buf = executed & 1u; sc->path = kSortLsd; }
         __syncthreads();
-        publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0);
+        publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0, mirror);
     }
 }
 

@@ -131,6 +131,15 @@ class GpuContext:
         """Sort the keys of a frame that ran with FRAME_CULL | FRAME_SORT_LATER (lets the count exchange overlap the sort)."""
         self._check(self._lib.astre_gpu_sort(self._h, stream))
 
+    def set_counts_mirror(self, ptr0, ptr1):
+        """Frame k also writes its per-view counts to device buffer ptr[k & 1] (k = frame_index()); 0, 0 switches it off."""
+        self._check(self._lib.astre_gpu_set_counts_mirror(self._h, int(ptr0) or None, int(ptr1) or None))
+
+    def frame_index(self):
+        v = C.c_uint64()
+        self._check(self._lib.astre_gpu_frame_index(self._h, C.byref(v)))
+        return int(v.value)
+
     def last_sort_path(self):
         """0 = no sort ran, 1 = bucket sort, 2 = LSD radix fallback (decided on the device)."""
         v = C.c_uint32(0)

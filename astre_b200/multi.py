@@ -85,48 +85,59 @@ def device_view(ptr, n, typestr, device):
 class CountExchange:
     """The per-frame exchange of SURVEY.md 8e, kept OFF the frame's critical path.
 
-    Per frame, on the frame's stream: one tiny copy of the shard's per-view counts into a staging slot (the
-    library zeroes its counters when the next frame begins).  Everything else runs on a side stream while the
-    next frames compute: NCCL all-gather of the staged counts -> [world_size, n_views] table ->
-    astre_gpu_global_offsets_dev (this rank's segment offsets and the per-view totals, on the device).
-    Two slots alternate; a slot is reused only after its exchange has finished (an event wait that is already
-    satisfied in steady state).  `finish()` joins the side stream back (end of a timed region, or before reading).
-    No host round trip anywhere."""
+    The library mirrors every frame's per-view counts into one of two device slots (astre_gpu_set_counts_mirror; the
+    frame's last kernel writes them, so the frame stays one CUDA graph).  After a frame the caller's stream only
+    records an event; everything else runs on a side stream while the next frames compute: NCCL all-gather of the
+    slot -> [world_size, n_views] table -> astre_gpu_global_offsets_dev (this rank's segment offsets and the per-view
+    totals, on the device).  A slot is rewritten two frames later, and only after its exchange has finished (an
+    event wait that is already satisfied in steady state).  `finish()` joins the side stream back (end of a timed
+    region, or before reading).  No host round trip anywhere."""
 
     def __init__(self, ctx, n_counts, group=None, device=None, rank_major=False):
         self.ctx, self.group, self.n, self.rank_major = ctx, group, int(n_counts), bool(rank_major)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.counts_dev = device_view(ctx.device_counts_ptr(), self.n, "<i4", self.device)
-        self.stage = [torch.zeros(self.n, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.slot = [torch.zeros(self.n, dtype=torch.int32, device=self.device) for _ in range(2)]
         self.table = [torch.zeros((self.world, self.n), dtype=torch.int32, device=self.device) for _ in range(2)]
         self.offsets = [torch.zeros(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
         self.totals = [torch.zeros(self.n, dtype=torch.int64, device=self.device) for _ in range(2)]
         self.side = torch.cuda.Stream(device=self.device)
-        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.framed = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
-        self.frame = 0
+        self.busy = [False, False]
+        self.last_slot = None
+        ctx.set_counts_mirror(self.slot[0].data_ptr(), self.slot[1].data_ptr())
 
-    def enqueue(self):
-        """Call right after the frame's cull (counts final) on the frame's stream."""
-        p = self.frame & 1
+    def close(self):
+        self.finish()
+        torch.cuda.synchronize(self.device)
+        self.ctx.set_counts_mirror(0, 0)
+
+    def before_frame(self):
+        """Call before ctx.frame(): the slot the coming frame writes must not be in use by an exchange any more."""
+        p = (self.ctx.frame_index() + 1) & 1
+        if self.busy[p]:
+            torch.cuda.current_stream(self.device).wait_event(self.done[p])
+            self.busy[p] = False
+
+    def after_frame(self):
+        """Call after ctx.frame() on the frame's stream: hands the frame's counts to the side stream."""
+        p = self.ctx.frame_index() & 1
         main = torch.cuda.current_stream(self.device)
-        if self.frame >= 2:
-            main.wait_event(self.done[p])                       # slot p: exchange of frame-2 finished
-        self.stage[p].copy_(self.counts_dev, non_blocking=True)
-        self.staged[p].record(main)
-        self.side.wait_event(self.staged[p])
+        self.framed[p].record(main)
+        self.side.wait_event(self.framed[p])
         with torch.cuda.stream(self.side):
             if self.world > 1:
-                dist.all_gather_into_tensor(self.table[p].view(-1), self.stage[p], group=self.group)
+                dist.all_gather_into_tensor(self.table[p].view(-1), self.slot[p], group=self.group)
             else:
-                self.table[p].view(-1).copy_(self.stage[p], non_blocking=True)
+                self.table[p].view(-1).copy_(self.slot[p], non_blocking=True)
             self.ctx.global_offsets_dev(self.table[p].data_ptr(), self.world, self.rank, self.n,
                                         self.offsets[p].data_ptr(), self.totals[p].data_ptr(), self.side.cuda_stream,
                                         rank_major=self.rank_major)
             self.done[p].record(self.side)
-        self.frame += 1
+        self.busy[p] = True
+        self.last_slot = p
         return p
 
     def finish(self):
@@ -134,7 +145,7 @@ class CountExchange:
 
     def last(self):
         """(all_counts [world, n], offsets [n], totals [n]) of the most recent frame, on the host (synchronises)."""
-        p = (self.frame - 1) & 1
+        p = self.last_slot
         self.done[p].synchronize()
         return (self.table[p].cpu().numpy().astype(np.uint32), self.offsets[p].cpu().numpy().astype(np.uint64),
                 self.totals[p].cpu().numpy().astype(np.uint64))

@@ -291,11 +291,13 @@ class Bench:
         self.ctx.set_stream(self.stream.cuda_stream)
         self.rank_major = s.n_worlds > 1          # whole-world shards: the global list is the concatenation of the ranks' lists
         self.exchange = multi.CountExchange(self.ctx, self.n_counts, rank_major=self.rank_major) if world > 1 and name != "config1" else None
-        # single-GPU steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
-        self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph and self.exchange is None else 0)
+        # steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
+        self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph else 0)
 
     def close(self):
         self.torch.cuda.synchronize()
+        if self.exchange:
+            self.exchange.close()
         self.ctx.close()
 
     def barrier(self):
@@ -304,14 +306,14 @@ class Bench:
         self.torch.cuda.synchronize()
 
     def step(self):
-        g = self.gpu
         if self.exchange is None:
             self.ctx.frame(self.frame_flags)
             return
-        # counts are final when the cull kernel ends: stage them, hand the exchange to the side stream, sort
-        self.ctx.frame(g.FRAME_TRANSFORM | g.FRAME_CULL | g.FRAME_SORT_LATER)
-        self.exchange.enqueue()
-        self.ctx.sort()
+        # the frame's last kernel mirrors the counts into a slot; the exchange (all-gather + offsets) runs on a side
+        # stream while the next frames compute
+        self.exchange.before_frame()
+        self.ctx.frame(self.frame_flags)
+        self.exchange.after_frame()
 
     def max_over_ranks(self, x, op="max"):
         t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")

@@ -355,6 +355,12 @@ ASTRE_API void astre_global_offsets_rank_major(const uint32_t *all_counts, uint3
 /* The same on the device and stream-ordered, for an all-gathered count table that never leaves the GPU
  * (all pointers are device pointers; offsets_dev / view_totals_dev may be NULL): the per-frame exchange of
  * SURVEY.md 8e then needs no host round trip.  rank_major != 0: the layout of astre_global_offsets_rank_major.  stream: cudaStream_t cast to void* (NULL = the context's). */
+/* Frame k (astre_gpu_frame_index, counted from 1 and wrapping at 2^27) also leaves its per-(world, view) counts in
+ * dev_slot[k & 1] (device memory of the caller, uint32[n_worlds * views] each): the exchange of SURVEY.md 8e can
+ * then read them on another stream while frame k+1 -- which zeroes the live counters -- is already running.
+ * Two NULLs switch the mirror off.  Synchronises. */
+ASTRE_API int astre_gpu_set_counts_mirror(astre_gpu_ctx *ctx, void *dev_slot0, void *dev_slot1);
+ASTRE_API int astre_gpu_frame_index(const astre_gpu_ctx *ctx, uint64_t *index);
 ASTRE_API int astre_gpu_global_offsets_dev(astre_gpu_ctx *ctx, const uint32_t *all_counts_dev, uint32_t world_size,
                                            uint32_t rank, uint32_t n_views, uint32_t rank_major, uint64_t *offsets_dev,
                                            uint64_t *view_totals_dev, void *stream);

@@ -506,6 +506,37 @@ def test_frame_graph_replays_equal_plain_frames(oracle):
             assert np.array_equal(oracle_lib.bits(ctx.read_world(0, scene.n)), oracle_lib.bits(o_world))
 
 
+def test_count_exchange_single_rank(oracle):
+    """multi.CountExchange without peers: the counts mirror (two device slots written by the frame's last kernel), the
+    side-stream table and the device-side segment offsets of every frame, while frames keep being enqueued."""
+    import torch
+    from astre_b200 import multi
+    for scene, rank_major in ((scenes.config3(200_000), False), (scenes.config5(n_worlds=32, entities_per_world=1024), True)):
+        n_counts = scene.n_worlds * scene.views_per_world
+        with GpuContext(scene.n, max_views=scene.views_per_world) as ctx:
+            scenes.load_into(ctx, scene)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                ctx.set_stream(stream.cuda_stream)
+                ex = multi.CountExchange(ctx, n_counts, rank_major=rank_major)
+                for k in range(5):
+                    if k == 3:                                   # the scene changes between frames
+                        scene.pos = (scene.pos * np.float32(0.5)).astype(np.float32)
+                        ctx.update_trs_range(0, scene.n, scene.pos, scene.rot, scene.scale)
+                    ex.before_frame()
+                    ctx.frame(gpu.FRAME_ALL | (gpu.FRAME_GRAPH if k % 2 else 0))
+                    ex.after_frame()
+                    if k in (2, 4):
+                        table, off, tot = ex.last()
+                        _, _, o_counts = oracle.frame(scene)
+                        assert np.array_equal(table[0], o_counts)
+                        h_off, h_tot = gpu.global_offsets(table, 0, rank_major)
+                        assert np.array_equal(off, h_off) and np.array_equal(tot, h_tot)
+                        assert np.array_equal(ctx.read_counts(), o_counts)
+                ex.close()
+            ctx.set_stream(None)
+
+
 def test_read_draw_list(oracle):
     s = scenes.config3(200_000)
     with GpuContext(s.n, max_views=5) as ctx:
