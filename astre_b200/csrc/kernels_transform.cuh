@@ -426,19 +426,54 @@ template <bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, ASTRE_CONE_MIN_BLOCKS)
 k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint2 *__restrict__ ranges, const uint32_t n_levels)
 {
+    constexpr uint32_t kBufKeys = CULL ? 3072u : 1u;          // per-CTA key buffer: ONE global reservation per flush
     __shared__ float4 s_scratch[kBlockThreads * 4];
+    __shared__ unsigned long long s_kbuf[kBufKeys];
     __shared__ uint32_t s_counts[32];
+    __shared__ uint32_t s_kfill;
+    __shared__ unsigned long long s_kbase;
     const int lane = threadIdx.x & 31;
     const uint32_t F = CULL ? P.views_per_world : 0u;
     const bool one_world = P.n_worlds <= 1;
+    // every warp reserving its keys with an atomic on the frame's one key counter serialises at the L2 (a third of a
+    // million same-address atomics on configuration 2); buffered per CTA it is a few hundred
+    const bool buffered = CULL && F * kBlockThreads <= kBufKeys / 2u;
     if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_kfill = 0;
     cudaGridDependencySynchronize();
     __syncthreads();
+    auto flush = [&]() {                                       // block-wide; callers synchronise before and after
+        const uint32_t fill = s_kfill;
+        if (fill) {
+            if (threadIdx.x == 0) s_kbase = atomicAdd(&P.ctl->key_total, (unsigned long long)fill);
+            __syncthreads();
+            const unsigned long long base = s_kbase;
+            for (uint32_t i = threadIdx.x; i < fill; i += kBlockThreads) {
+                const unsigned long long k = s_kbuf[i], pos = base + i;
+                if (pos < P.key_cap) {
+                    P.keys[pos] = k;
+                    if (bp.bits) atomicAdd(&P.bins[bin_digit(bp, k)], 1u);
+                } else {
+                    P.ctl->overflow = 1u;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_kfill = 0;
+        }
+    };
     for (uint32_t level = 0; level < n_levels; ++level) {
         const uint2 r = __ldg(ranges + (size_t)blockIdx.x * n_levels + level);
         const uint32_t first = r.x, n = r.y - r.x;
         const uint32_t n_round = (n + 31u) & ~31u;
-        for (uint32_t i = threadIdx.x; i < n_round; i += kBlockThreads) {
+        for (uint32_t i0 = 0; i0 < n_round; i0 += kBlockThreads) {
+            if (buffered) {                                    // room for everything this round can emit?
+                __syncthreads();
+                const uint32_t fill_now = s_kfill;             // read by everyone before anyone appends again: one decision per CTA
+                __syncthreads();
+                if (fill_now + F * kBlockThreads > kBufKeys) { flush(); __syncthreads(); }
+            }
+            const uint32_t i = i0 + threadIdx.x;
+            if (i >= n_round) continue;                        // whole warps only: n_round is a multiple of 32
             const bool active = i < n;
             const uint32_t slot = active ? first + i : first;
             const float *t = P.tiles + tile_index(slot, 0);
@@ -479,17 +514,33 @@ k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint
             const uint32_t incl = warp_incl_scan(cnt, lane);
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             if (total) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&P.ctl->key_total, (unsigned long long)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
                 if (!one_world)
                     for (uint32_t v = 0; v < F; ++v)
                         if ((vis[0] >> v) & 1u) atomicAdd(&P.counts[(size_t)world * F + v], 1u);
-                if (cnt) emit_keys<1>(P, bp, V, world, wb, vis, meta, local, base + (incl - cnt), one_world ? s_counts : nullptr);
+                if (buffered) {
+                    uint32_t sbase = 0;
+                    if (lane == 0) sbase = atomicAdd(&s_kfill, total);
+                    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+                    uint32_t at = sbase + (incl - cnt), mv = vis[0];
+                    while (mv) {
+                        const uint32_t v = __ffs(mv) - 1;
+                        mv &= mv - 1;
+                        s_kbuf[at++] = make_key(P.world_bits, world, v, (meta[0] >> 11) & 255u, meta[0] & 2047u,
+                                                depth14(wb[0], V.depth(v), V.depth_scale(v)), local[0]);
+                        if (one_world) atomicAdd(&s_counts[v], 1u);
+                    }
+                } else {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&P.ctl->key_total, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (cnt) emit_keys<1>(P, bp, V, world, wb, vis, meta, local, base + (incl - cnt), one_world ? s_counts : nullptr);
+                }
             }
         }
         __syncthreads();     // the next level reads this level's matrices (same CTA: block-scope ordering is enough)
     }
+    if (buffered) { flush(); }
+    __syncthreads();
     if (CULL && one_world && threadIdx.x < F && s_counts[threadIdx.x]) atomicAdd(&P.counts[threadIdx.x], s_counts[threadIdx.x]);
 }
 
