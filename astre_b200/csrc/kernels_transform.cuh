@@ -465,10 +465,17 @@ k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint
         const uint2 r = __ldg(ranges + (size_t)blockIdx.x * n_levels + level);
         const uint32_t first = r.x, n = r.y - r.x;
         const uint32_t n_round = (n + 31u) & ~31u;
+        // room in the key buffer: checked once per level when the whole level fits, else before every round of 256
+        const bool level_fits = buffered && (unsigned long long)n_round * F <= kBufKeys / 2u;
+        if (level_fits) {
+            const uint32_t fill_now = s_kfill;                 // (after the barrier that ended the previous level)
+            __syncthreads();                                   // read by everyone before anyone appends again: one decision per CTA
+            if (fill_now + n_round * F > kBufKeys) { flush(); __syncthreads(); }
+        }
         for (uint32_t i0 = 0; i0 < n_round; i0 += kBlockThreads) {
-            if (buffered) {                                    // room for everything this round can emit?
+            if (buffered && !level_fits) {
                 __syncthreads();
-                const uint32_t fill_now = s_kfill;             // read by everyone before anyone appends again: one decision per CTA
+                const uint32_t fill_now = s_kfill;
                 __syncthreads();
                 if (fill_now + F * kBlockThreads > kBufKeys) { flush(); __syncthreads(); }
             }

@@ -2,7 +2,9 @@
 """Prints the headline metrics, opcode mix and stall breakdown of an .ncu-rep (first profiled launch)."""
 import collections, csv, re, subprocess, sys
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+KFILTER = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []   # which kernel of a multi-kernel report
+KERNEL_INDEX = 0
+raw = subprocess.run(["ncu", "-i", rep] + KFILTER + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
@@ -10,17 +12,19 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__inst_executed.sum', 'sm__cycles_elapsed.max', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'launch__grid_size', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct']
-print("kernel:", rows[2][hdr.index('Kernel Name')][:100])
+R = rows[2 + KERNEL_INDEX]
+print("kernel:", R[hdr.index('Kernel Name')][:100])
 for w in want:
     if w in hdr:
         i = hdr.index(w)
-        print(f"  {w:70s} {units[i]:10s} {rows[2][i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        print(f"  {w:70s} {units[i]:10s} {R[i]}")
+src = subprocess.run(["ncu", "-i", rep] + KFILTER + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
-h = rows[hi[0]]
-end = hi[1] - 1 if len(hi) > 1 else len(rows)
-body = [r for r in rows[hi[0] + 1:end] if len(r) == len(h)]
+k = min(KERNEL_INDEX, len(hi) - 1)
+h = rows[hi[k]]
+end = hi[k + 1] - 1 if len(hi) > k + 1 else len(rows)
+body = [r for r in rows[hi[k] + 1:end] if len(r) == len(h)]
 ci = {n: i for i, n in enumerate(h)}
 tot = sum(int(r[ci['Instructions Executed']]) for r in body)
 op = collections.Counter()
