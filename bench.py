@@ -338,8 +338,24 @@ class Bench:
             self.exchange.finish()          # the last exchanges end inside the timed region
         e1.record(self.stream)
         self.barrier()
-        ms_step = self.max_over_ranks(e0.elapsed_time(e1)) / steps
+        own_ms = e0.elapsed_time(e1) / steps
+        ms_step = self.max_over_ranks(own_ms)
         launches = int(self.max_over_ranks(self.ctx.launch_count - launches0, "sum"))
+        self.scaling_detail = None
+        if self.exchange:
+            # what the exchange and the slowest GPU cost: the same loop without the exchange, and the spread over ranks
+            self.barrier()
+            e0.record(self.stream)
+            for _ in range(steps):
+                self.ctx.frame(self.frame_flags)
+            e1.record(self.stream)
+            self.barrier()
+            plain = e0.elapsed_time(e1) / steps
+            self.scaling_detail = {"ms_per_step_min_over_ranks": -self.max_over_ranks(-own_ms), "ms_per_step_max_over_ranks": ms_step,
+                                   "without_exchange_ms_min_over_ranks": -self.max_over_ranks(-plain),
+                                   "without_exchange_ms_max_over_ranks": self.max_over_ranks(plain),
+                                   "note": "ranks advance in step (a count slot is reused only when its exchange is done), so every rank "
+                                           "runs at the pace of the slowest GPU; exchange cost = max - without_exchange max"}
         # torch-issued kernels inside the step at N > 1: staging copy + NCCL all-gather per frame (not counted as ours)
         return ms_step, launches
 
@@ -466,7 +482,7 @@ def run_workload(name, rank, local_rank, world, args, torch, dist, steps, warmup
         out = {"workload": b.workload, "scaling": b.scaling, "value": b.total_entities / (ms_step * 1e-3), "unit": "entities/s",
                "ms_per_step": ms_step, "entities_per_gpu": b.n, "views": b.F, "visible_keys_rank0": int(b.total_keys),
                "sort_path": {0: "none", 1: "bucket", 2: "lsd-fallback"}[b.sort_path], "gpu_launches": launches,
-               "frame_as_cuda_graph": bool(b.frame_flags & b.gpu.FRAME_GRAPH),
+               "frame_as_cuda_graph": bool(b.frame_flags & b.gpu.FRAME_GRAPH), "scaling_detail": b.scaling_detail,
                "roofline": b.roofline(kernel_ms, ms_step), "e2e": b.end_to_end(e2e_steps)}
         parity, cpu = b.parity_and_cpu(cpu_reps, not args.no_cpu_baseline)
         out["parity"], out["cpu_baseline"] = parity, cpu
@@ -543,6 +559,7 @@ def main():
                                    + ("; NCCL all-gather of per-shard visible counts + device-side segment offsets every step, off the critical path" if world > 1 else ""),
                        "entities_per_gpu": n, "views": head["views"], "visible_keys_rank0": head["visible_keys_rank0"],
                        "sort_path": head["sort_path"], "frame_as_cuda_graph": head["frame_as_cuda_graph"],
+                       "scaling_detail": head["scaling_detail"],
                        "l2": f"inputs ({n * 44 / 1e6:.0f} MB/GPU) and outputs ({n * 64 / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no flush"
                              if n * 108 > 4 * 126e6 else "working set fits the 126 MB L2: launch-latency regime, stated as such",
                        "extra_workloads": extras},
