@@ -27,7 +27,7 @@ EntityMirror::EntityMirror(std::uint32_t max_entities)
     : _max(max_entities), _entity_at(max_entities, 0), _pos(3 * (std::size_t)max_entities, 0.0f),
       _rot(4 * (std::size_t)max_entities, 0.0f), _scl(3 * (std::size_t)max_entities, 1.0f),
       _mesh(max_entities, 0), _shader(max_entities, 0), _parent(max_entities, ASTRE_NO_PARENT),
-      _flags(max_entities, 0), _state(max_entities, 0), _color(max_entities)
+      _flags(max_entities, 0), _state(max_entities, 0), _has(max_entities, 0), _color(max_entities)
 {
 }
 
@@ -57,6 +57,7 @@ std::uint32_t EntityMirror::spawn(Entity e, const TransformComponent &t, const V
     P[0] = p.x; P[1] = p.y; P[2] = p.z;
     R[0] = q.x; R[1] = q.y; R[2] = q.z; R[3] = q.w;
     S[0] = s.x; S[1] = s.y; S[2] = s.z;
+    _has[slot] = (std::uint8_t)((t.position ? 1u : 0u) | (t.rotation ? 2u : 0u) | (t.scale ? 4u : 0u));
     _parent[slot] = parent ? _slot_of.at(parent) : ASTRE_NO_PARENT;
     // visual_system.cpp:23-30: a proxy exists only if both names resolve
     std::uint8_t flags = 0;
@@ -97,6 +98,7 @@ void EntityMirror::setPosition(Entity e, Vec3 p)
     const std::uint32_t s = _slot_of.at(e);
     float *P = &_pos[3 * (std::size_t)s];
     P[0] = p.x; P[1] = p.y; P[2] = p.z;
+    _has[s] |= 1u;
     markDirty(s); _state[s] |= kDirtyTrs;
 }
 void EntityMirror::setRotation(Entity e, Quat q)
@@ -104,6 +106,7 @@ void EntityMirror::setRotation(Entity e, Quat q)
     const std::uint32_t s = _slot_of.at(e);
     float *R = &_rot[4 * (std::size_t)s];
     R[0] = q.x; R[1] = q.y; R[2] = q.z; R[3] = q.w;
+    _has[s] |= 2u;
     markDirty(s); _state[s] |= kDirtyTrs;
 }
 void EntityMirror::setScale(Entity e, Vec3 v)
@@ -111,6 +114,7 @@ void EntityMirror::setScale(Entity e, Vec3 v)
     const std::uint32_t s = _slot_of.at(e);
     float *S = &_scl[3 * (std::size_t)s];
     S[0] = v.x; S[1] = v.y; S[2] = v.z;
+    _has[s] |= 4u;
     markDirty(s); _state[s] |= kDirtyTrs;
 }
 void EntityMirror::setVisible(Entity e, bool visible)
@@ -271,8 +275,8 @@ void GpuVisualSystem::run(float, Frame &frame)
     std::vector<std::uint64_t> keys(total);
     std::vector<float> world(16 * (std::size_t)total);
     std::uint64_t got = 0;
-    check(_ctx, astre_gpu_read_all_keys(_ctx, keys.data(), total, &got), "astre_gpu_read_all_keys");
-    if (total) check(_ctx, astre_gpu_read_visible_world(_ctx, 0, total, world.data()), "astre_gpu_read_visible_world");
+    // sorted keys and, in the same order, uModel of their entities: one call, one copy each
+    check(_ctx, astre_gpu_read_draw_list(_ctx, keys.data(), world.data(), total, &got), "astre_gpu_read_draw_list");
 
     frame.draw_lists.resize(n_views);
     std::size_t k = 0;
@@ -292,10 +296,13 @@ void GpuVisualSystem::run(float, Frame &frame)
             p.useTexture = false;
             p.uColor = _mirror.color(slot);
             std::memcpy(p.uModel.data(), &world[16 * k], 64);
+            // "used for interpolation" (visual_system.cpp:49-52): raw proto reads, so an absent field is zeros here
+            // (not TransformSystem's default) -- kept as the reference has it
             const float *P = _mirror.position(slot), *R = _mirror.rotation(slot), *S = _mirror.scale(slot);
-            p.position = Vec3{P[0], P[1], P[2]};
-            p.rotation = Quat{R[0], R[1], R[2], R[3]};
-            p.scale = Vec3{S[0], S[1], S[2]};
+            const std::uint8_t has = _mirror.present(slot);
+            p.position = (has & 1u) ? Vec3{P[0], P[1], P[2]} : Vec3{0, 0, 0};
+            p.rotation = (has & 2u) ? Quat{R[0], R[1], R[2], R[3]} : Quat{0, 0, 0, 0};
+            p.scale = (has & 4u) ? Vec3{S[0], S[1], S[2]} : Vec3{0, 0, 0};
         }
     }
 

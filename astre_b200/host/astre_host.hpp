@@ -143,6 +143,10 @@ public:
     std::uint32_t mesh(std::uint32_t slot) const { return _mesh[slot]; }
     std::uint32_t shader(std::uint32_t slot) const { return _shader[slot]; }
     const Vec4 &color(std::uint32_t slot) const { return _color[slot]; }
+    // which of position / rotation / scale the component carries (proto has_*): bit 0 / 1 / 2.  TransformSystem
+    // substitutes defaults for absent ones (transform_system.cpp:24-49); VisualSystem copies the raw -- zero --
+    // proto values into the proxy (visual_system.cpp:50-52).  Both behaviours are kept.
+    std::uint8_t present(std::uint32_t slot) const { return _has[slot]; }
 
 private:
     void markDirty(std::uint32_t slot);
@@ -152,7 +156,7 @@ private:
     std::vector<std::uint32_t> _free;
     std::vector<float> _pos, _rot, _scl;
     std::vector<std::uint32_t> _mesh, _shader, _parent;
-    std::vector<std::uint8_t> _flags, _state;   // _state: bit0 dirty TRS, bit1 dirty flags, bit2 fresh
+    std::vector<std::uint8_t> _flags, _state, _has;   // _state: bit0 dirty TRS, bit1 dirty flags, bit2 fresh
     std::vector<Vec4> _color;
     std::vector<std::uint32_t> _dirty, _fresh;
 };

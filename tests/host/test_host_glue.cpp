@@ -355,6 +355,128 @@ static void test_frame_interpolation(uint32_t n)
     EXPECT(r.view_matrix[12] == fa.view_matrix[12] * (1.0f - alpha) + fb.view_matrix[12] * alpha);
 }
 
+// ---- against the reference's own systems (oracle/_ref/libastre_ref.so: its sources compiled unmodified) ----------
+#include <dlfcn.h>
+namespace ref {
+using u64 = uint64_t;
+void *lib = nullptr;
+void *(*world_create)();
+void (*world_destroy)(void *);
+int (*add_transforms)(void *, uint32_t, const u64 *, const uint8_t *, const float *, const float *, const float *);
+int (*set_trs)(void *, uint32_t, const u64 *, const float *, const float *, const float *);
+int (*add_visual)(void *, u64, int, const char *, const char *, const float *);
+int (*add_camera)(void *, u64, float, float, float, float);
+int (*register_vertex_buffer)(void *, const char *, u64);
+int (*register_shader)(void *, const char *, u64);
+int (*run_transform)(void *);
+int (*get_transforms)(void *, uint32_t, const u64 *, float *, float *, float *, float *);
+int (*run_camera)(void *, u64, int, float *, float *, float *);
+int (*run_visual)(void *, int);
+u64 (*proxy_count)(void *, int);
+int (*get_proxy)(void *, int, u64, u64 *, float *);
+template <class F> bool sym(F &f, const char *name) { f = reinterpret_cast<F>(dlsym(lib, name)); return f != nullptr; }
+bool load(const char *argv0)
+{
+    std::string dir(argv0);
+    const size_t slash = dir.rfind('/');
+    dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+    lib = dlopen((dir + "/../../../oracle/_ref/libastre_ref.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return false;
+    return sym(world_create, "ref_world_create") && sym(world_destroy, "ref_world_destroy") && sym(add_transforms, "ref_add_transforms") &&
+           sym(set_trs, "ref_set_trs") && sym(add_visual, "ref_add_visual") && sym(add_camera, "ref_add_camera") &&
+           sym(register_vertex_buffer, "ref_register_vertex_buffer") && sym(register_shader, "ref_register_shader") &&
+           sym(run_transform, "ref_run_transform") && sym(get_transforms, "ref_get_transforms") && sym(run_camera, "ref_run_camera") &&
+           sym(run_visual, "ref_run_visual") && sym(proxy_count, "ref_proxy_count") && sym(get_proxy, "ref_get_proxy");
+}
+}  // namespace ref
+
+// The same world in the glue (GPU) and in the reference's Registry; TransformSystem, CameraSystem and VisualSystem on
+// both sides.  Every field the reference's systems write must come out identical; the glue's proxies are the
+// reference's proxies restricted to the entities that survive a view (the documented narrowing).
+static void test_against_reference_build(uint32_t n)
+{
+    void *rw = ref::world_create();
+    EXPECT(rw != nullptr);
+    if (!rw) return;
+    World w(n + 1);
+    const char *meshes[] = {"cube_prefab", "icosphere2_prefab", "cone_prefab", "dome_prefab", "quad_prefab", "ghost_mesh"};
+    const char *all_meshes[] = {"cube_prefab", "quad_prefab", "cone_prefab", "cylinder_prefab", "icosphere1_prefab", "icosphere2_prefab",
+                                "icosphere3_prefab", "dome_prefab"};
+    for (uint64_t i = 0; i < 8; ++i) ref::register_vertex_buffer(rw, all_meshes[i], i);
+    ref::register_shader(rw, "deferred_shader", 0);
+    ref::register_shader(rw, "basic_shader", 1);
+    std::mt19937 rng(99);
+    std::uniform_real_distribution<float> P(-60.0f, 60.0f), Q(-1.0f, 1.0f), S(0.25f, 3.0f);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint64_t id = 1000 + i;
+        TransformComponent t;
+        float p[3] = {0, 0, 0}, q[4] = {0, 0, 0, 0}, s[3] = {0, 0, 0};
+        uint8_t has = 0;
+        if (i % 7) { p[0] = P(rng); p[1] = P(rng) * 0.2f; p[2] = P(rng) - 50.0f; t.position = Vec3{p[0], p[1], p[2]}; has |= 1; }
+        if (i % 3) {
+            q[0] = Q(rng); q[1] = Q(rng); q[2] = Q(rng); q[3] = Q(rng);
+            if (i % 8) { const float l = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); for (float &c : q) c /= l; }   // some stay un-normalised
+            t.rotation = Quat{q[0], q[1], q[2], q[3]}; has |= 2;
+        }
+        if (i % 5) { s[0] = S(rng); s[1] = S(rng); s[2] = (i % 9) ? S(rng) : -S(rng); t.scale = Vec3{s[0], s[1], s[2]}; has |= 4; }
+        VisualComponent v;
+        v.vertex_buffer_name = meshes[i % 6];
+        v.shader_name = (i % 4) ? "deferred_shader" : ((i % 8) ? "basic_shader" : "ghost_shader");
+        v.visible = (i % 11) != 0;
+        float color[4] = {0.1f * (float)(i % 10), 0.5f, 0.25f, 1.0f};
+        if (i % 2) v.color = Vec4{color[0], color[1], color[2], color[3]};
+        const bool has_visual = (i % 13) != 0;
+        w.mirror.spawn(id, t, has_visual ? &v : nullptr, &w.names);
+        EXPECT(ref::add_transforms(rw, 1, &id, &has, p, q, s) == 0);
+        if (has_visual) EXPECT(ref::add_visual(rw, id, v.visible ? 1 : 0, v.vertex_buffer_name.c_str(), v.shader_name.c_str(), (i % 2) ? color : nullptr) == 0);
+    }
+    {   // the camera entity of level_0.json
+        const uint64_t id = 5;
+        const uint8_t has = 1;
+        const float p[3] = {0, 5, 15}, q[4] = {0, 0, 0, 0}, s[3] = {0, 0, 0};
+        TransformComponent cam; cam.position = Vec3{0, 5, 15};
+        w.mirror.spawn(id, cam, nullptr, nullptr);
+        ref::add_transforms(rw, 1, &id, &has, p, q, s);
+        ref::add_camera(rw, id, 60.0f, 0.1f, 1000.0f, 1.7f);
+        w.cameras.active_camera_entity = 5;
+    }
+    Frame frame;
+    w.transforms.run(0.1f);
+    EXPECT(ref::run_transform(rw) == 0);
+    bool mats = true, basis = true;
+    for (uint32_t s = 0; s < w.mirror.slotCount(); ++s) {
+        const uint64_t id = w.mirror.entityAt(s);
+        TransformComponent out;
+        w.transforms.read(id, out);
+        float m[16], f[3], u[3], r[3];
+        if (ref::get_transforms(rw, 1, &id, m, f, u, r) != 0) { mats = false; break; }
+        mats &= same_bits(m, out.transform_matrix.data(), 16);
+        basis &= same_bits(f, &out.forward.x, 3) && same_bits(u, &out.up.x, 3) && same_bits(r, &out.right.x, 3);
+    }
+    EXPECT(mats);
+    EXPECT(basis);
+    w.cameras.run(0.1f, frame);
+    float view[16], proj[16], cpos[3];
+    EXPECT(ref::run_camera(rw, 5, 0, view, proj, cpos) == 0);
+    EXPECT(same_bits(view, frame.view_matrix.data(), 16) && same_bits(proj, frame.proj_matrix.data(), 16));
+    EXPECT(same_bits(cpos, &frame.camera_position.x, 3));
+    w.visuals.run(0.1f, frame);
+    EXPECT(ref::run_visual(rw, 0) == 0);
+    EXPECT(frame.render_proxies.size() > n / 50 && frame.render_proxies.size() <= ref::proxy_count(rw, 0));
+    bool proxies_ok = true;
+    for (const auto &[id, p] : frame.render_proxies) {
+        uint64_t u[5];
+        float f[30];
+        if (ref::get_proxy(rw, 0, id, u, f) != 0) { proxies_ok = false; break; }      // the reference has no proxy for it
+        proxies_ok &= (u[0] != 0) == p.visible && u[1] == p.phases && u[2] == p.vertex_buffer && u[3] == p.shader && (u[4] != 0) == p.useTexture;
+        proxies_ok &= same_bits(f + 0, &p.position.x, 3) && same_bits(f + 3, &p.rotation.x, 4) && same_bits(f + 7, &p.scale.x, 3);
+        proxies_ok &= same_bits(f + 10, p.uModel.data(), 16) && same_bits(f + 26, &p.uColor.x, 4);
+        if (!proxies_ok) { std::printf("proxy %llu differs from the reference build\n", (unsigned long long)id); break; }
+    }
+    EXPECT(proxies_ok);
+    ref::world_destroy(rw);
+}
+
 int main(int argc, char **argv)
 {
     const bool cpu_only = argc > 1 && std::string(argv[1]) == "--cpu";
@@ -363,6 +485,8 @@ int main(int argc, char **argv)
         test_level0_like_world();
         test_random_world(20000);
         test_frame_interpolation(5000);
+        if (ref::load(argv[0])) test_against_reference_build(20000);
+        else std::printf("note: oracle/_ref/libastre_ref.so not found -- comparison with the reference build skipped\n");
     }
     std::printf("%s: %d checks, %d failures%s\n", g_failures ? "FAILED" : "PASSED", g_checks, g_failures, cpu_only ? " (cpu-only subset)" : "");
     return g_failures ? 1 : 0;
