@@ -96,10 +96,19 @@ struct astre_gpu_ctx {
 
     // ASTRE_FRAME_GRAPH: the frame's launches as one instantiated CUDA graph
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph_obj = nullptr;                    // kept: its node handles address the exec's kernel nodes
     FramePlan graph_plan;
-    uint64_t graph_views_version = 0, graph_levels_version = 0, views_version = 1, levels_version = 1;
+    // views_version: the CONTENT of the view records changed (same counts, same buffers) -- a single-world frame has
+    // them as a kernel parameter of its one fused launch, which is patched in place (cudaGraphExecKernelNodeSetParams);
+    // params_version: anything else a captured launch has baked in (buffers reallocated, mesh table, view count, mirror)
+    uint64_t graph_views_version = 0, graph_params_version = 0, graph_levels_version = 0;
+    uint64_t views_version = 1, params_version = 1, levels_version = 1;
+    bool capturing = false;
+    uint32_t graph_vs_launches = 0;                     // fused launches of the captured frame that read the ViewSet parameter
+    cudaGraphNode_t graph_vs_node = nullptr;
+    struct { FrameParams P; BinPlan bp; LevelTable LT; const void *fn; unsigned grid; } graph_vs_args;
     cudaStream_t graph_stream = nullptr;
-    uint32_t graph_launches = 0, graph_captures = 0;
+    uint32_t graph_launches = 0, graph_captures = 0, graph_view_patches = 0;
     bool last_timed = false;             // the last frame recorded the cull events (not when replayed from a graph)
 
     // f3: global draw list across GPUs
@@ -154,6 +163,7 @@ struct astre_gpu_ctx {
     uint32_t h_overflow = 0, h_result_buf = 0;
 
     cudaEvent_t ev_begin = nullptr, ev_cull0 = nullptr, ev_cull1 = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_views = nullptr;      // recorded after the last upload of view records
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     int fused_blocks_per_sm = 2;
@@ -571,7 +581,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
     for (void *p : ptrs) if (p) cudaFree(p);
     for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
-    cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1 };
+    cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1, ctx->ev_views };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -581,6 +591,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph_obj) cudaGraphDestroy(ctx->graph_obj);
     delete ctx;
 }
 
@@ -743,7 +754,7 @@ int astre_gpu_set_mesh_bounds(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->n_meshes = n_meshes;
-    ++ctx->views_version;
+    ++ctx->params_version;
     return ASTRE_OK;
 }
 
@@ -767,7 +778,9 @@ int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t en
     CK(cudaSetDevice(ctx->device));
     const uint64_t n_rec = (uint64_t)n_worlds * views_per_world;
     if (n_rec > 0xFFFFFFFFull) return fail(ctx, ASTRE_ERR_INVALID, "too many view records");
-    CK(cudaStreamSynchronize(ctx->stream));
+    const bool reallocated = n_rec > ctx->cap_view_records || n_rec > ctx->cap_counts;
+    if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));   // frames enqueued on a caller's stream
+    if (reallocated) CK(cudaStreamSynchronize(ctx->stream));
     if (n_rec > ctx->cap_view_records) {
         CK(cudaFree(ctx->d_views)); ctx->d_views = nullptr;
         CK(cudaMalloc(&ctx->d_views, n_rec * sizeof(ViewDev)));
@@ -783,10 +796,19 @@ int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t en
     std::vector<astre_host::ViewHost> recs(n_rec);
     for (uint64_t i = 0; i < n_rec; ++i)
         astre_host::extract_view(clip16 + 16 * i, phase_mask[i % views_per_world] & 15u, &recs[i]);
-    if (n_rec) CK(cudaMemcpy(ctx->d_views, recs.data(), n_rec * sizeof(ViewDev), cudaMemcpyHostToDevice));
+    // stream-ordered after the frames that still read the old records; `recs` is pageable, so the runtime stages it
+    // before returning (no synchronisation: a camera that moves every frame must not stall the pipeline)
+    if (n_rec) {
+        CK(cudaMemcpyAsync(ctx->d_views, recs.data(), n_rec * sizeof(ViewDev), cudaMemcpyHostToDevice, ctx->stream));
+        if (!ctx->ev_views) CK(cudaEventCreateWithFlags(&ctx->ev_views, cudaEventDisableTiming));
+        CK(cudaEventRecord(ctx->ev_views, ctx->stream));        // a frame on another stream waits for it
+    }
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
     if (n_worlds == 1 && views_per_world) std::memcpy(ctx->h_viewset.v, recs.data(), views_per_world * sizeof(ViewDev));
-    ++ctx->views_version;                         // a captured frame graph has the old records and pointers baked in
+    // a captured frame graph: new record CONTENT is patched in / read from global memory; anything else is captured again
+    ++ctx->views_version;
+    if (reallocated || ctx->n_worlds != n_worlds || ctx->views_per_world != views_per_world ||
+        ctx->entities_per_world != (n_worlds > 1 ? entities_per_world : 0u)) ++ctx->params_version;
     ctx->n_worlds = n_worlds;
     ctx->entities_per_world = n_worlds > 1 ? entities_per_world : 0;
     ctx->views_per_world = views_per_world;
@@ -867,6 +889,11 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
             else if (hier) fn = worlds ? (const void *)k_frame_fused<true, true, true> : (const void *)k_frame_fused<true, false, true>;
             else fn = worlds ? (const void *)k_frame_fused<false, true, true> : (const void *)k_frame_fused<false, false, true>;
             void *args[] = { (void *)&P, (void *)&ctx->h_viewset, (void *)&bp, (void *)&LT };
+            if (ctx->capturing && cull && !worlds) {          // this launch reads the view records from its parameters
+                ++ctx->graph_vs_launches;
+                ctx->graph_vs_args.P = P; ctx->graph_vs_args.bp = bp; ctx->graph_vs_args.LT = LT;
+                ctx->graph_vs_args.fn = fn; ctx->graph_vs_args.grid = g;
+            }
             if (LT.n > 1) {
                 launch_err = cudaLaunchCooperativeKernel(fn, dim3(g), dim3(kBlockThreads), args, kFusedSmemBytes, s);
             } else {
@@ -1014,35 +1041,68 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     if ((stage_flags & ASTRE_FRAME_BASIS) && !ctx->d_basis)
         CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
 
+    if (s != ctx->stream && ctx->ev_views) CK(cudaStreamWaitEvent(s, ctx->ev_views, 0));
     CK(cudaEventRecord(ctx->ev_begin, s));
     if (stage_flags & ASTRE_FRAME_GRAPH) {
         // One cudaGraphLaunch instead of 6+ launches: what matters for small frames, where the launches ARE the frame.
         // Captured when the plan, the views, the hierarchy or the stream changed (an exec update when the topology is the same).
-        const bool stale = !ctx->graph_exec || !same_plan(fp, ctx->graph_plan) || ctx->graph_views_version != ctx->views_version ||
+        const bool stale = !ctx->graph_exec || !same_plan(fp, ctx->graph_plan) || ctx->graph_params_version != ctx->params_version ||
                            ctx->graph_levels_version != ctx->levels_version || ctx->graph_stream != s;
-        if (stale) {
+        bool views_changed = ctx->graph_views_version != ctx->views_version;
+        if (!stale && views_changed && ctx->graph_vs_launches <= 1) {
+            // the camera moved: kernels that read the records from global memory see the new ones already; the one
+            // launch that has them as a parameter is patched in place
+            if (ctx->graph_vs_launches == 1 && ctx->graph_vs_node) {
+                void *args[] = { (void *)&ctx->graph_vs_args.P, (void *)&ctx->h_viewset, (void *)&ctx->graph_vs_args.bp, (void *)&ctx->graph_vs_args.LT };
+                cudaKernelNodeParams kp{};
+                kp.func = const_cast<void *>(ctx->graph_vs_args.fn);
+                kp.gridDim = dim3(ctx->graph_vs_args.grid); kp.blockDim = dim3(kBlockThreads);
+                kp.sharedMemBytes = kFusedSmemBytes; kp.kernelParams = args; kp.extra = nullptr;
+                if (cudaGraphExecKernelNodeSetParams(ctx->graph_exec, ctx->graph_vs_node, &kp) == cudaSuccess) views_changed = false;
+                else cudaGetLastError();
+            } else if (ctx->graph_vs_launches == 0) {
+                views_changed = false;
+            }
+            if (!views_changed) { ctx->graph_views_version = ctx->views_version; ++ctx->graph_view_patches; }
+        }
+        if (stale || views_changed) {
             cudaGraph_t g = nullptr;
-            CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            ctx->capturing = true;
+            ctx->graph_vs_launches = 0;
+            ctx->graph_vs_node = nullptr;
+            const cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+            if (be != cudaSuccess) { ctx->capturing = false; return fail(ctx, ASTRE_ERR_CUDA, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(be)); }
             const uint64_t launches_before = ctx->launches;
             const int rc = enqueue_frame(ctx, fp, s, false);
             const cudaError_t ce = cudaStreamEndCapture(s, &g);
+            ctx->capturing = false;
             ctx->graph_launches = (uint32_t)(ctx->launches - launches_before);
             ctx->launches = launches_before;
             if (rc != ASTRE_OK) { if (g) cudaGraphDestroy(g); return rc; }
             if (ce != cudaSuccess) return fail(ctx, ASTRE_ERR_CUDA, "graph capture of the frame failed: %s", cudaGetErrorString(ce));
-            bool updated = false;
-            if (ctx->graph_exec) {
-                cudaGraphExecUpdateResultInfo info;
-                updated = cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess;
-                if (!updated) { cudaGetLastError(); cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            if (ctx->graph_obj) { cudaGraphDestroy(ctx->graph_obj); ctx->graph_obj = nullptr; }
+            const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+            if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; return fail(ctx, ASTRE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+            ctx->graph_obj = g;
+            if (ctx->graph_vs_launches == 1) {          // find the node of that launch
+                size_t n_nodes = 0;
+                CK(cudaGraphGetNodes(g, nullptr, &n_nodes));
+                std::vector<cudaGraphNode_t> nodes(n_nodes);
+                CK(cudaGraphGetNodes(g, nodes.data(), &n_nodes));
+                uint32_t found = 0;
+                for (cudaGraphNode_t nd : nodes) {
+                    cudaGraphNodeType ty;
+                    if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+                    cudaKernelNodeParams kp{};
+                    if (cudaGraphKernelNodeGetParams(nd, &kp) != cudaSuccess) { cudaGetLastError(); continue; }
+                    if (kp.func == ctx->graph_vs_args.fn) { ctx->graph_vs_node = nd; ++found; }
+                }
+                if (found != 1) ctx->graph_vs_node = nullptr;     // ambiguous: a change of views captures again
             }
-            if (!updated) {
-                const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
-                if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; return fail(ctx, ASTRE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
-            }
-            cudaGraphDestroy(g);
             ctx->graph_plan = fp;
             ctx->graph_views_version = ctx->views_version;
+            ctx->graph_params_version = ctx->params_version;
             ctx->graph_levels_version = ctx->levels_version;
             ctx->graph_stream = s;
             ++ctx->graph_captures;
@@ -1197,7 +1257,7 @@ int astre_gpu_set_counts_mirror(astre_gpu_ctx *ctx, void *dev_slot0, void *dev_s
     if (int rc = astre_gpu_sync(ctx)) return rc;
     ctx->counts_mirror.slot[0] = static_cast<uint32_t *>(dev_slot0);
     ctx->counts_mirror.slot[1] = static_cast<uint32_t *>(dev_slot1);
-    ++ctx->views_version;              // kernel parameters of a captured frame graph
+    ++ctx->params_version;             // kernel parameters of a captured frame graph
     return ASTRE_OK;
 }
 
@@ -1205,6 +1265,56 @@ int astre_gpu_frame_index(const astre_gpu_ctx *ctx, uint64_t *index)
 {
     if (!ctx || !index) return ASTRE_ERR_INVALID;
     *index = ctx->epoch;
+    return ASTRE_OK;
+}
+
+namespace {
+__global__ void k_debug_adopt_keys(FrameControl *ctl, const unsigned long long *__restrict__ keys, unsigned long long n,
+                                   uint32_t *__restrict__ bins, const __grid_constant__ BinPlan bp)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->key_total = n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        atomicAdd(&bins[bin_digit(bp, keys[i])], 1u);
+}
+}  // namespace
+
+int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t n, uint64_t live_mask, uint32_t bin_bits,
+                              uint64_t *sorted_out, uint32_t *path_out)
+{
+    if (!ctx || (n && (!keys || !sorted_out))) return ASTRE_ERR_INVALID;
+    if (n > ctx->max_keys) return fail(ctx, ASTRE_ERR_CAPACITY, "%llu keys exceed the capacity %llu", (unsigned long long)n, (unsigned long long)ctx->max_keys);
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    cudaStream_t s = ctx->stream;
+    FramePlan fp;
+    std::memset(&fp, 0, sizeof fp);
+    fp.plan = make_sort_plan(live_mask);
+    fp.bp = make_bin_plan(live_mask, std::max<uint32_t>(2u, std::min<uint32_t>(bin_bits, ctx->cap_bin_bits)));
+    ctx->epoch = ctx->epoch + 1;                             // in step with the device-side frame number (k_frame_begin)
+    if (ctx->epoch >= kEpochWrap) {
+        const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
+        CK(cudaMemsetAsync(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long), s));
+        CK(cudaMemsetAsync(ctx->d_sc->scan_state, 0, sizeof(ctx->d_sc->scan_state), s));
+        ctx->epoch = 1;
+    }
+    const uint32_t n_bins = fp.bp.bits ? (1u << fp.bp.bits) : 0u;
+    k_frame_begin<<<64, 256, 0, s>>>(ctx->d_ctl, ctx->d_sc, ctx->d_counts, 0u, ctx->d_bins, n_bins);
+    CK_LAUNCH();
+    if (n) CK(cudaMemcpyAsync(ctx->d_keys[0], keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    k_debug_adopt_keys<<<(unsigned)ctx->sm_count * 4u, 256, 0, s>>>(ctx->d_ctl, ctx->d_keys[0], n, ctx->d_bins, fp.bp);
+    CK_LAUNCH();
+    if (int rc = launch_sort(ctx, fp.bp, fp.plan, 0u, s)) return rc;
+    CK(cudaStreamSynchronize(s));
+    uint32_t buf = 0, path = 0;
+    if (fp.bp.bits) {
+        CK(cudaMemcpy(&buf, &ctx->d_sc->result_buf, sizeof buf, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&path, &ctx->d_sc->path, sizeof path, cudaMemcpyDeviceToHost));
+    }
+    if (n) CK(cudaMemcpy(sorted_out, ctx->d_keys[buf & 1u], n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (path_out) *path_out = path;
+    ctx->frame_done = false;                                 // the key buffers no longer hold a frame's list
+    ctx->results_cached = false;
+    ctx->sort_pending = false;
     return ASTRE_OK;
 }
 

@@ -140,6 +140,15 @@ class GpuContext:
         self._check(self._lib.astre_gpu_frame_index(self._h, C.byref(v)))
         return int(v.value)
 
+    def debug_sort_keys(self, keys, live_mask, bin_bits):
+        """Test hook: the frame's key sort on an arbitrary set of unique keys -> (sorted keys, path)."""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        out = np.empty(len(keys), np.uint64)
+        path = C.c_uint32(0)
+        self._check(self._lib.astre_gpu_debug_sort_keys(self._h, _ptr(keys, C.c_uint64), len(keys), int(live_mask), int(bin_bits),
+                                                        _ptr(out, C.c_uint64), C.byref(path)))
+        return out, int(path.value)
+
     def last_sort_path(self):
         """0 = no sort ran, 1 = bucket sort, 2 = LSD radix fallback (decided on the device)."""
         v = C.c_uint32(0)

@@ -407,16 +407,23 @@ class Bench:
             ctx.read_counts(cnt_np)
             return ctx.read_draw_list(keys_np, vis_np)       # sorted keys + the visible entities' world matrices
 
+        def set_views():           # the engine hands the frame's view / light-space matrices over every tick (visual_system glue)
+            if s.n_worlds > 1:
+                ctx.set_world_views(s.n_worlds, s.entities_per_world, s.clip, s.masks)
+            else:
+                ctx.set_views(s.clip[0], s.masks)
+
         def all_dirty():
             ctx.update_trs_range(0, n, pos_np, rot_np, scl_np)
+            set_views()
             ctx.frame(self.frame_flags)
             return read_results()
 
         ms, nk = timed(all_dirty, steps)
         out = {"value": self.total_entities / (ms * 1e-3), "unit": "entities/s", "ms_per_step": ms,
                "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(self.n_counts * 4 + nk * 8 + nk * 64),
-               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_frame + astre_gpu_read_counts + "
-                       "astre_gpu_read_draw_list (sorted keys + world matrices of the visible entities)"}
+               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_set_views + astre_gpu_frame + "
+                       "astre_gpu_read_counts + astre_gpu_read_draw_list (sorted keys + world matrices of the visible entities)"}
         # the case the mirror was built for: a dirty subset pushed as a slot list (astre_gpu_update_trs)
         rng = np.random.default_rng(7)
         for pct in (1, 10):
@@ -427,6 +434,7 @@ class Bench:
 
             def dirty():
                 ctx.update_trs(sl_h, p_h, r_h, s_h)
+                set_views()
                 ctx.frame(self.frame_flags)
                 return read_results()
 

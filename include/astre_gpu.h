@@ -176,6 +176,12 @@ ASTRE_API int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream);
  * Appendix B): the reference has no draw-order sort (deferred_shading.cpp:115,151 walk a hash map).
  * Synchronises. */
 ASTRE_API int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path);
+/* Test hook of the spec-defined key sort (no reference counterpart): sorts n UNIQUE 64-bit keys whose varying bits lie
+ * inside live_mask with a bucket digit of bin_bits bits, through exactly the kernels a frame uses (bucket path or,
+ * chosen on the device, the LSD fallback); *path_out as astre_gpu_last_sort_path.  Invalidates the last frame's
+ * results.  Lets tests drive the sort with key sets no scene produces. */
+ASTRE_API int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t n, uint64_t live_mask,
+                                        uint32_t bin_bits, uint64_t *sorted_out, uint32_t *path_out);
 ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
 /* Makes every later call on ctx (mirror updates, frames with stream == NULL,
  * read-backs) enqueue on the caller's cudaStream_t instead of the context's own

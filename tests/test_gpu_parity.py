@@ -376,9 +376,11 @@ def test_interpolate(oracle):
     print(f"f1 rotation block: max {worst:.3f} ULP of the column scale")
 
 
-def test_stress_moving_camera_and_dirty_sets(oracle):
+@pytest.mark.parametrize("graph", [False, True])
+def test_stress_moving_camera_and_dirty_sets(oracle, graph):
     """Many frames on one context: the camera turns, entities move, flags flip -- every frame equals the oracle
-    (shakes out stale state between frames: look-back epochs, histograms, counters, key buffers)."""
+    (shakes out stale state between frames: look-back epochs, bucket counts, counters, key buffers).  With the frame
+    replayed as a CUDA graph the view records of every frame are patched into the captured launch."""
     s = scenes.config3(120_000)
     s.pos = (s.pos * np.float32(0.1)).astype(np.float32)
     rng = np.random.default_rng(21)
@@ -394,7 +396,7 @@ def test_stress_moving_camera_and_dirty_sets(oracle):
             fl = rng.choice(s.n, 500, replace=False).astype(np.uint32)
             s.flags[fl] ^= 1
             ctx.update_flags(fl, s.flags[fl])
-            ctx.frame()
+            ctx.frame(gpu.FRAME_ALL | (gpu.FRAME_GRAPH if graph else 0))
             keys, counts = ctx.read_all_keys(), ctx.read_counts()
             if it % 4 == 3 or it < 2:
                 _, o_keys, o_counts = oracle.frame(s)
@@ -449,6 +451,63 @@ def test_sort_paths(oracle, mode, monkeypatch):
                     assert path == 2, (mode, scene.name, path)                   # crowded buckets: the fallback, chosen on the device
                 elif mode in ("auto", "bins22"):
                     assert path == 1, (mode, scene.name, path)
+
+
+def _spread(values, mask):
+    """pdep: deposits the low bits of `values` into the set bits of `mask` (LSB first)."""
+    out = np.zeros(len(values), np.uint64)
+    j = 0
+    for b in range(64):
+        if (mask >> b) & 1:
+            out |= ((values >> np.uint64(j)) & np.uint64(1)) << np.uint64(b)
+            j += 1
+    return out
+
+
+def test_sort_fuzz_arbitrary_key_sets():
+    """The key sort on key sets no scene produces (astre_gpu_debug_sort_keys): every size around the tile / chunk /
+    bucket boundaries, every bucket width, uniform / clustered / sequential / one-bucket distributions, fragmented
+    live masks -- against numpy's sort.  Crowded sets must take the LSD fallback by themselves."""
+    rng = np.random.default_rng(5)
+    masks = [0x38_1C_07_FF_FC_FF_FF_FF, (1 << 46) - 1, 0xFFF0_0000_0FFF_F0FF, 0x0000_0003_FFFF_FFFF, 0x8000_0000_0000_0001 | (0xFFFFF << 20)]
+    sizes = [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 2047, 2048, 2049, 3071, 3072, 3073, 4095, 4096, 4097,
+             5000, 8191, 8192, 8193, 50_000, 262_144, 1_000_003]
+    with GpuContext(1024, max_views=1, max_keys=1_100_000) as ctx:
+        for mask in masks:
+            live = bin(mask).count("1")
+            for n in sizes:
+                if n > (1 << min(live, 40)) or (n > 8193 and mask not in masks[:2]):
+                    continue
+                for kind in ("uniform", "clustered", "sequential", "one_bucket"):
+                    if kind == "uniform":
+                        v = rng.choice(1 << min(live, 40), size=n, replace=False).astype(np.uint64) if n < 300_000 else \
+                            np.unique(rng.integers(0, 1 << min(live, 40), size=2 * n, dtype=np.uint64))[:n]
+                        if live > 40:
+                            v = v << np.uint64(live - 40) | rng.integers(0, 1 << (live - 40), size=len(v), dtype=np.uint64)
+                    elif kind == "clustered":                   # most keys share their top bits: big buckets
+                        v = np.unique((rng.integers(0, 7, size=2 * n + 8, dtype=np.uint64) << np.uint64(live - 3)) |
+                                      rng.integers(0, max(4 * n, 16), size=2 * n + 8, dtype=np.uint64))[:n]
+                    elif kind == "sequential":
+                        v = np.arange(n, dtype=np.uint64)[::-1].copy()
+                    else:                                        # all keys differ only in their lowest bits
+                        v = rng.permutation(n).astype(np.uint64)
+                    if len(v) < n:
+                        continue
+                    keys = _spread(v, mask)
+                    rng.shuffle(keys)
+                    want = np.sort(keys)
+                    for bits in ((2, 8, 13, 17, 22) if n <= 8193 else (8, 17)):
+                        got, path = ctx.debug_sort_keys(keys, mask, bits)
+                        assert np.array_equal(got, want), (hex(mask), n, kind, bits, path)
+                        if n > 1:
+                            assert path in (1, 2)
+                        if kind == "one_bucket" and n > 2048 and bits <= live - 22:
+                            assert path == 2, (n, bits)        # > 2048 keys in one bucket: the device picks the fallback
+        # frames still work on the same context afterwards
+        s = scenes.config1(1000)
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        assert np.all(np.diff(ctx.read_all_keys().astype(np.int64)) > 0)
 
 
 def test_sort_bucket_count_follows_the_key_count(oracle):
