@@ -109,6 +109,7 @@ struct astre_gpu_ctx {
     struct { FrameParams P; BinPlan bp; LevelTable LT; const void *fn; unsigned grid; } graph_vs_args;
     cudaStream_t graph_stream = nullptr;
     uint32_t graph_launches = 0, graph_captures = 0, graph_view_patches = 0;
+    bool last_gathered = false;          // the last frame ran k_gather_list (ASTRE_FRAME_GATHER) on its sorted list
     bool last_timed = false;             // the last frame recorded the cull events (not when replayed from a graph)
 
     // f3: global draw list across GPUs
@@ -979,6 +980,18 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
                               (const FrameControl *)ctx->d_ctl, (const SortControl *)ctx->d_sc, ctx->d_res, ctx->counts_mirror));
         CK_LAUNCH();
     }
+    if ((stage_flags & ASTRE_FRAME_GATHER) && cull && ctx->d_gather) {
+        cudaLaunchAttribute pdl;
+        pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg{};
+        cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1; cfg.gridDim = dim3((unsigned)ctx->sm_count * 4u); cfg.blockDim = dim3(256);
+        CK(cudaLaunchKernelEx(&cfg, k_gather_list, (const unsigned long long *)ctx->d_keys[0], (const unsigned long long *)ctx->d_keys[1],
+                              (const SortControl *)ctx->d_sc, (const FrameControl *)ctx->d_ctl, (unsigned long long)ctx->max_keys,
+                              (sort_now && bp.bits) ? 1u : 0u, (const float4 *)ctx->d_world, ctx->d_gather,
+                              (unsigned long long)ctx->cap_gather, ctx->world_bits, ctx->entities_per_world, ctx->d_res));
+        CK_LAUNCH();
+    }
     return ASTRE_OK;
 }
 
@@ -1040,6 +1053,11 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     }
     if ((stage_flags & ASTRE_FRAME_BASIS) && !ctx->d_basis)
         CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
+    if ((stage_flags & ASTRE_FRAME_GATHER) && !ctx->d_gather) {          // room for a typical list; longer ones are gathered on read
+        ctx->cap_gather = std::min<uint64_t>(ctx->max_keys, 1ull << 20);
+        CK(cudaMalloc(&ctx->d_gather, ctx->cap_gather * 64));
+        ++ctx->params_version;
+    }
 
     if (s != ctx->stream && ctx->ev_views) CK(cudaStreamWaitEvent(s, ctx->ev_views, 0));
     CK(cudaEventRecord(ctx->ev_begin, s));
@@ -1119,6 +1137,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     ctx->pending_plan = fp.plan;
     ctx->pending_bins = fp.bp;
     ctx->last_sorted = fp.sort_now && fp.bp.bits != 0;
+    ctx->last_gathered = (stage_flags & ASTRE_FRAME_GATHER) && fp.cull && fp.sort_now;
     ctx->frame_done = true;
     ctx->results_cached = false;
     ctx->last_flags = fp.stage_flags;
@@ -1135,6 +1154,7 @@ int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream)
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     if (int rc = launch_sort(ctx, ctx->pending_bins, ctx->pending_plan, 0u, s)) return rc;
     ctx->last_sorted = ctx->pending_bins.bits != 0;
+    ctx->last_gathered = false;
     ctx->last_flags = (ctx->last_flags & ~(uint32_t)ASTRE_FRAME_SORT_LATER) | ASTRE_FRAME_SORT;
     ctx->sort_pending = false;
     ctx->results_cached = false;
@@ -1429,6 +1449,7 @@ int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_
         ctx->d_gather = nullptr;
         CK(cudaMalloc(&ctx->d_gather, n * 64));
         ctx->cap_gather = n;
+        ++ctx->params_version;                  // a captured frame graph has the old buffer baked in
     }
     cudaStream_t s = ctx->last_stream;
     const uint32_t grid = std::min<uint32_t>(ceil_div(n * 4, 256), (uint32_t)ctx->sm_count * 8);
@@ -1451,12 +1472,24 @@ int astre_gpu_read_draw_list(astre_gpu_ctx *ctx, uint64_t *keys, float *world16,
     const uint64_t n = std::min(have, cap);
     if (!n) return ASTRE_OK;
     cudaStream_t s = ctx->last_stream;
+    if (ctx->last_gathered && ctx->h_res->list_n == have) {          // short list: the frame left it in host memory
+        if (keys) std::memcpy(keys, ctx->h_res->list_keys, n * sizeof(uint64_t));
+        if (world16) std::memcpy(world16, ctx->h_res->list_world, n * 64);
+        return ASTRE_OK;
+    }
+    if (ctx->last_gathered && have <= ctx->cap_gather) {             // gathered inside the frame: two copies, no launch
+        if (keys) CK(cudaMemcpyAsync(keys, ctx->d_keys[ctx->h_result_buf], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        if (world16) CK(cudaMemcpyAsync(world16, ctx->d_gather, n * 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return ASTRE_OK;
+    }
     if (world16) {
         if (ctx->cap_gather < n) {
             if (ctx->d_gather) CK(cudaFree(ctx->d_gather));
             ctx->d_gather = nullptr;
             CK(cudaMalloc(&ctx->d_gather, n * 64));
             ctx->cap_gather = n;
+            ++ctx->params_version;              // a captured frame graph has the old buffer baked in
         }
         const uint32_t grid = std::min<uint32_t>(ceil_div(n * 4, 256), (uint32_t)ctx->sm_count * 8);
         k_gather_world<<<grid, 256, 0, s>>>(ctx->d_keys[ctx->h_result_buf], 0ull, n, ctx->d_world, ctx->d_gather,

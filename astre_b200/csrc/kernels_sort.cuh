@@ -199,12 +199,17 @@ __device__ __forceinline__ void scan_counts_block(const uint32_t *__restrict__ c
 // reading a frame's results then costs one stream synchronisation and no copy (small frames are all latency).
 // key_total doubles as the hint that sizes the next frame's buckets.
 constexpr uint32_t kInlineCounts = 256;
+constexpr uint32_t kInlineList = 4096;                  // draw lists up to this length also land in host memory (ASTRE_FRAME_GATHER)
+constexpr uint32_t kNoInlineList = 0xFFFFFFFFu;
 struct FrameResultHost {
     unsigned long long key_total;
     uint32_t overflow, result_buf, path;
     uint32_t n_counts;                                  // counts / offsets mirrored below (0: too many, copy them from the device)
     uint32_t counts[kInlineCounts];
     unsigned long long offsets[kInlineCounts + 1];
+    uint32_t list_n, list_pad;                          // k_gather_list: length of the list mirrored below, or kNoInlineList
+    unsigned long long list_keys[kInlineList];
+    float4 list_world[kInlineList * 4];
 };
 
 // Optional device-side copy of the per-view counts, alternating between two caller buffers by frame parity: what a
@@ -226,6 +231,7 @@ __device__ __forceinline__ void publish_results(FrameResultHost *res, const Fram
         res->overflow = ctl->overflow;
         res->result_buf = sc->result_buf;
         res->path = sc->path;
+        res->list_n = kNoInlineList;                    // k_gather_list, if the frame has one, runs after this
     }
     if (with_counts) {
         const bool inl = n_counts <= kInlineCounts;
@@ -666,6 +672,36 @@ k_sort_lsd_all(unsigned long long *__restrict__ buf0, unsigned long long *__rest
         __syncthreads();
         publish_results(res, ctl, sc, counts, offsets, n_counts, n_counts != 0, mirror);
     }
+}
+
+// ASTRE_FRAME_GATHER: the world matrices of the draw list's entities in list order (what VisualSystem::run puts into
+// render_proxies[e].inputs.in_mat4["uModel"], visual_system.cpp:47), produced inside the frame so that reading the list
+// back needs no further launch; short lists also land, keys and matrices, in mapped host memory (no copy at all).
+__global__ void __launch_bounds__(256)
+k_gather_list(const unsigned long long *__restrict__ buf0, const unsigned long long *__restrict__ buf1, const SortControl *sc,
+              const FrameControl *ctl, const unsigned long long key_cap, const uint32_t sorted,
+              const float4 *__restrict__ world, float4 *__restrict__ out, const unsigned long long out_cap,
+              const uint32_t world_bits, const uint32_t entities_per_world, FrameResultHost *res)
+{
+    cudaGridDependencySynchronize();
+    const unsigned long long n = min(ctl->key_total, key_cap);
+    const unsigned long long *keys = (sorted && sc->result_buf) ? buf1 : buf0;
+    const unsigned long long m = min(n, out_cap);
+    const bool inl = res != nullptr && n <= kInlineList && ctl->key_total <= key_cap;
+    const uint32_t local_bits = 26u - world_bits;
+    for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < m * 4ull;
+         j += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[j >> 2];
+        const uint32_t local = (uint32_t)(key & ((1ull << local_bits) - 1ull));
+        const uint32_t w = world_bits ? (uint32_t)(key >> (64 - world_bits)) : 0u;
+        const float4 v = world[(size_t)(w * entities_per_world + local) * 4 + (j & 3)];
+        out[j] = v;
+        if (inl) {
+            res->list_world[j] = v;
+            if ((j & 3) == 0) res->list_keys[j >> 2] = key;
+        }
+    }
+    if (res && blockIdx.x == 0 && threadIdx.x == 0) res->list_n = inl ? (uint32_t)n : kNoInlineList;
 }
 
 }  // namespace astre

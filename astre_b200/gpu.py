@@ -5,7 +5,7 @@ import numpy as np
 
 from ._lib import AstreError, DrawRun, MeshBounds, load_library
 
-FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER, FRAME_GRAPH = 1, 2, 4, 8, 16, 32
+FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER, FRAME_GRAPH, FRAME_GATHER = 1, 2, 4, 8, 16, 32, 64
 FRAME_ALL = 7
 
 PHASE_OPAQUE, PHASE_TRANSPARENT, PHASE_SHADOW_CASTER, PHASE_DEBUG = 1, 2, 4, 8

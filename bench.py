@@ -293,6 +293,7 @@ class Bench:
         self.exchange = multi.CountExchange(self.ctx, self.n_counts, rank_major=self.rank_major) if world > 1 and name != "config1" else None
         # steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
         self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph else 0)
+        self.e2e_flags = self.frame_flags | gpu.FRAME_GATHER     # end-to-end steps read the list's matrices back: gathered in-frame
 
     def close(self):
         self.torch.cuda.synchronize()
@@ -416,13 +417,13 @@ class Bench:
         def all_dirty():
             ctx.update_trs_range(0, n, pos_np, rot_np, scl_np)
             set_views()
-            ctx.frame(self.frame_flags)
+            ctx.frame(self.e2e_flags)
             return read_results()
 
         ms, nk = timed(all_dirty, steps)
         out = {"value": self.total_entities / (ms * 1e-3), "unit": "entities/s", "ms_per_step": ms,
                "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(self.n_counts * 4 + nk * 8 + nk * 64),
-               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_set_views + astre_gpu_frame + "
+               "what": "astre_gpu_update_trs_range(all entities, pinned host) + astre_gpu_set_views + astre_gpu_frame(ALL | GATHER) + "
                        "astre_gpu_read_counts + astre_gpu_read_draw_list (sorted keys + world matrices of the visible entities)"}
         # the case the mirror was built for: a dirty subset pushed as a slot list (astre_gpu_update_trs)
         rng = np.random.default_rng(7)
@@ -435,7 +436,7 @@ class Bench:
             def dirty():
                 ctx.update_trs(sl_h, p_h, r_h, s_h)
                 set_views()
-                ctx.frame(self.frame_flags)
+                ctx.frame(self.e2e_flags)
                 return read_results()
 
             ms_d, nk_d = timed(dirty, steps)

@@ -75,6 +75,9 @@ enum {
     ASTRE_FRAME_GRAPH     = 1u << 5,  /* replay the frame's launches as ONE CUDA graph (captured again when the   */
                                       /* plan, views, hierarchy or stream change); astre_gpu_last_cull_ms is then  */
                                       /* unavailable.  For small frames, where launch latency is the frame.        */
+    ASTRE_FRAME_GATHER    = 1u << 6,  /* with CULL | SORT: also gather the world matrices of the draw list's entities in */
+                                      /* list order inside the frame (astre_gpu_read_draw_list then launches nothing;  */
+                                      /* lists of <= 4096 keys are left in host memory by the frame itself)            */
     ASTRE_FRAME_ALL       = 7u
 };
 

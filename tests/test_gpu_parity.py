@@ -596,6 +596,37 @@ def test_count_exchange_single_rank(oracle):
             ctx.set_stream(None)
 
 
+def test_gather_inside_the_frame(oracle):
+    """ASTRE_FRAME_GATHER: the list's world matrices are produced by the frame itself; short lists (<= 4096 keys) arrive
+    in host memory with no copy, longer ones need two copies and no launch, lists beyond the gather buffer fall back."""
+    for scene, flags in ((scenes.config1(), gpu.FRAME_ALL | gpu.FRAME_GATHER),                     # 1137 keys: inline
+                         (scenes.config1(), gpu.FRAME_ALL | gpu.FRAME_GATHER | gpu.FRAME_GRAPH),
+                         (scenes.config3(400_000), gpu.FRAME_ALL | gpu.FRAME_GATHER | gpu.FRAME_GRAPH),  # ~17k keys: device gather
+                         (scenes.config5(n_worlds=16, entities_per_world=2048), gpu.FRAME_ALL | gpu.FRAME_GATHER)):
+        o_world, o_keys, _ = oracle.frame(scene)
+        local_bits = 26 - max(int(np.ceil(np.log2(scene.n_worlds))), 0) if scene.n_worlds > 1 else 26
+        wshift = 64 - (26 - local_bits)
+        slots = (o_keys & np.uint64((1 << local_bits) - 1)).astype(np.int64)
+        if scene.n_worlds > 1:
+            slots += (o_keys >> np.uint64(wshift)).astype(np.int64) * scene.entities_per_world
+        with GpuContext(scene.n, max_views=scene.views_per_world) as ctx:
+            scenes.load_into(ctx, scene)
+            k, w = np.zeros(len(o_keys) + 8, np.uint64), np.zeros((len(o_keys) + 8, 16), np.float32)
+            for _ in range(3):
+                ctx.frame(flags)
+                n = ctx.read_draw_list(k, w)
+                assert n == len(o_keys) and np.array_equal(k[:n], o_keys)
+                assert np.array_equal(oracle_lib.bits(w[:n]), oracle_lib.bits(o_world[slots]))
+            launches = ctx.launch_count
+            ctx.frame(flags)
+            ctx.read_draw_list(k, w)
+            per_frame = ctx.launch_count - launches
+            ctx.frame(flags & ~gpu.FRAME_GATHER)
+            n = ctx.read_draw_list(k, w)                                # without the flag: gathered on read, same result
+            assert n == len(o_keys) and np.array_equal(oracle_lib.bits(w[:n]), oracle_lib.bits(o_world[slots]))
+            assert per_frame == 7                                       # reset, fused, scan, scatter, rank, fallback/counts, gather
+
+
 def test_read_draw_list(oracle):
     s = scenes.config3(200_000)
     with GpuContext(s.n, max_views=5) as ctx:
