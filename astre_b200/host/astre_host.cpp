@@ -266,7 +266,8 @@ void GpuVisualSystem::run(float, Frame &frame)
     astre_host::mat_mul(frame.proj_matrix.data(), frame.view_matrix.data(), &clip[0]);
     for (std::uint32_t v = 1; v < n_views; ++v) std::memcpy(&clip[16 * (std::size_t)v], frame.light_space_matrices[v - 1].data(), 64);
     check(_ctx, astre_gpu_set_views(_ctx, n_views, clip.data(), masks.data()), "astre_gpu_set_views");
-    check(_ctx, astre_gpu_frame(_ctx, ASTRE_FRAME_ALL, nullptr), "astre_gpu_frame");
+    // one graph launch; the list's uModel matrices are gathered inside the frame (short lists arrive in host memory)
+    check(_ctx, astre_gpu_frame(_ctx, ASTRE_FRAME_ALL | ASTRE_FRAME_GATHER | ASTRE_FRAME_GRAPH, nullptr), "astre_gpu_frame");
 
     std::vector<std::uint32_t> counts(n_views);
     check(_ctx, astre_gpu_read_counts(_ctx, counts.data()), "astre_gpu_read_counts");

@@ -11,7 +11,7 @@ hot path (fused transform + frustum cull + compaction + 64-bit draw-key sort) ov
              and the per-frame exchange of SURVEY.md 8e runs every step: NCCL all-gather of the per-shard visible
              counts + this rank's segment offsets (astre_gpu_global_offsets_dev), on a side stream, off the
              frame's critical path; the timed region ends only when the last exchange has finished.
-  extras     (config.extra_workloads, unless --no-extra) the other BASELINE.json configurations, each with its own
+  extras     (top-level key `extra_workloads`, unless --no-extra) the other BASELINE.json configurations, each with its own
              value / roofline / e2e / cpu_baseline / parity: config 1 (10k flat, N = 1 only), config 2 (1M, 8-level
              hierarchy; root-subtree shards), config 4 (67,108,864 flat FIXED, entity-range shards: strong
              scaling), config 5 (4096 worlds x 16,384 FIXED, whole-world shards: strong scaling).
@@ -23,11 +23,11 @@ matrices, all through the C ABI, inside the timed region (plus e2e_dirty_1pct / 
 mirror was built for).  After the timed regions every rank replays its shard with the CPU oracle and compares
 counts, the full sorted key list and every world matrix bit for bit (`parity`).
 
-`--impl reference` times the CPU side of the comparison on the SAME workload and size, on all host cores
-(threads set explicitly): the oracle port of the path (transform + cull + sort; the reference itself has no
-culling or sort, SURVEY.md section 0), plus, as a sub-figure, the reference's OWN TransformSystem::run +
-VisualSystem::run compiled from its sources (oracle/_ref) on its own hash-map storage, one thread.  That process
-never loads the product library.
+`--impl reference` times the CPU side of the comparison on the SAME workload and size (its `config` object equals
+the GPU arm's), on all host cores (threads set explicitly): the oracle port of the path (transform + cull + sort;
+the reference itself has no culling or sort, SURVEY.md section 0, so its own sources cannot run the whole path),
+plus, as a sub-figure, the reference's OWN TransformSystem::run + VisualSystem::run compiled from its sources
+(oracle/_ref) on its own hash-map storage, one thread.  That process never loads the product library.
 """
 import argparse
 import json
@@ -151,6 +151,15 @@ def make_workload(name, rank, world):
     raise SystemExit(f"unknown workload {name}")
 
 
+def headline_config(workload, n, views, visible_keys, world):
+    """The `config` object of the JSON line -- built by BOTH arms from the same values, so that they compare equal."""
+    return {"workload": workload + "; transform + frustum cull + compaction + 64-bit draw-key sort"
+                        + ("; per-frame exchange of per-shard visible counts (NCCL all-gather) and segment offsets" if world > 1 else ""),
+            "entities_per_gpu": int(n), "views": int(views), "visible_keys_rank0": int(visible_keys),
+            "l2": f"inputs ({n * 44 / 1e6:.0f} MB/GPU) and outputs ({n * 64 / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no flush"
+                  if n * 108 > 4 * 126e6 else "working set fits the 126 MB L2: launch-latency regime, stated as such"}
+
+
 def algorithmic_bytes(scene, total_keys):
     """HBM bytes one launch of the transform + cull kernel must move."""
     children = 0 if scene.parent is None else int((scene.parent != 0xFFFFFFFF).sum())
@@ -253,11 +262,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "entities/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload + "; transform + cull + 64-bit key sort", "entities_per_step": scene.n,
-                   "views": scene.views_per_world, "visible_keys": int(len(keys))},
+        "config": headline_config(workload, scene.n, scene.views_per_world, len(keys), world),
         "cpu_baseline": {"value": value, "unit": "entities/s", "cores": used, "kind": "port",
                          "sample": f"all {scene.n} entities of rank 0's workload per step (oracle/astre_oracle.c, OpenMP, "
-                                   f"{used} threads set explicitly); the reference itself has no cull or sort stage",
+                                   f"{used} threads set explicitly)",
+                         "why_port": "the path of the metric includes frustum culling, compaction and the key sort, which the reference "
+                                     "does not have (SURVEY.md section 0): the oracle port is the only CPU implementation of the whole "
+                                     "path; the part the reference does implement is timed from its own sources below",
                          "reference_systems_1thread": None if tick is None else {
                              "value": tick, "unit": "entities/s", "kind": "reference",
                              "what": "the reference's own TransformSystem::run + VisualSystem::run (oracle/_ref, compiled from "
@@ -564,14 +575,9 @@ def main():
             "metric": METRIC, "value": head["value"], "unit": "entities/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": head["workload"] + "; fused transform+cull+compact + 64-bit key sort"
-                                   + ("; NCCL all-gather of per-shard visible counts + device-side segment offsets every step, off the critical path" if world > 1 else ""),
-                       "entities_per_gpu": n, "views": head["views"], "visible_keys_rank0": head["visible_keys_rank0"],
-                       "sort_path": head["sort_path"], "frame_as_cuda_graph": head["frame_as_cuda_graph"],
-                       "scaling_detail": head["scaling_detail"],
-                       "l2": f"inputs ({n * 44 / 1e6:.0f} MB/GPU) and outputs ({n * 64 / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no flush"
-                             if n * 108 > 4 * 126e6 else "working set fits the 126 MB L2: launch-latency regime, stated as such",
-                       "extra_workloads": extras},
+            "config": headline_config(head["workload"], n, head["views"], head["visible_keys_rank0"], world),
+            "sort_path": head["sort_path"], "frame_as_cuda_graph": head["frame_as_cuda_graph"], "scaling_detail": head["scaling_detail"],
+            "extra_workloads": extras,
             "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"], "parity": head["parity"],
             "gpu_launches": head["gpu_launches"], "clocks": clocks,
         }

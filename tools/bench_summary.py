@@ -21,10 +21,10 @@ for path in sys.argv[1:]:
     d = json.loads(line)
     print(f"== {path}: n_gpus {d['n_gpus']} scaling {d['scaling']}")
     head = dict(d)
-    head["sort_path"] = d["config"].get("sort_path")
-    head["frame_as_cuda_graph"] = d["config"].get("frame_as_cuda_graph")
+    head["sort_path"] = d.get("sort_path", d["config"].get("sort_path"))
+    head["frame_as_cuda_graph"] = d.get("frame_as_cuda_graph", d["config"].get("frame_as_cuda_graph"))
     show("headline " + d["config"]["workload"][:40], head)
-    for k, v in d["config"].get("extra_workloads", {}).items():
+    for k, v in (d.get("extra_workloads") or d["config"].get("extra_workloads", {})).items():
         if "error" in v:
             print(k, v)
         else:
