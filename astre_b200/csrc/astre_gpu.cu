@@ -1367,8 +1367,12 @@ int astre_gpu_read_world(astre_gpu_ctx *ctx, uint32_t first, uint32_t count, flo
     if (!ctx || (count && !out)) return ASTRE_ERR_INVALID;
     if ((uint64_t)first + count > ctx->max_entities) return fail(ctx, ASTRE_ERR_INVALID, "slot range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    if (int rc = astre_gpu_sync(ctx)) return rc;
-    if (count) CK(cudaMemcpy(out, ctx->d_world + (size_t)first * 4, (size_t)count * 64, cudaMemcpyDeviceToHost));
+    // stream-ordered after the last frame, then one synchronisation of that stream (DMA straight into a pinned
+    // destination; a pageable one is staged by the runtime)
+    cudaStream_t s = ctx->last_stream ? ctx->last_stream : ctx->stream;
+    if (s != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
+    if (count) CK(cudaMemcpyAsync(out, ctx->d_world + (size_t)first * 4, (size_t)count * 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return ASTRE_OK;
 }
 

@@ -342,9 +342,11 @@ k_bin_scan(uint32_t *__restrict__ bins, const uint32_t n_bins, SortControl *sc, 
     // bucket e = [start, end) is the last one to start before every chunk boundary 1024 c in (start, end]
     const uint32_t e0 = idx4 * 4u;
     const uint32_t st[5] = { o0, o1, o2, o3, o4 };
+    // (a bucket beyond kMaxBucket sends the frame to the fallback, which needs no chunk table: skip its long walk)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        for (uint32_t cc = st[i] / kChunkKeys + 1u; cc * kChunkKeys <= st[i + 1]; ++cc) chunk_first[cc] = e0 + i + 1u;
+        if (st[i + 1] - st[i] <= kMaxBucket)
+            for (uint32_t cc = st[i] / kChunkKeys + 1u; cc * kChunkKeys <= st[i + 1]; ++cc) chunk_first[cc] = e0 + i + 1u;
     if (tile == 0 && threadIdx.x == 0) chunk_first[0] = 0u;
 }
 
