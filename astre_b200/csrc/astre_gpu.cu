@@ -171,6 +171,7 @@ struct astre_gpu_ctx {
     int cone_blocks_per_sm = 2;
     bool coop_launch = false;        // device supports cooperative launches (multi-level hierarchy launches)
     bool use_pdl = true;             // programmatic dependent launch for the sort chain (ASTRE_NO_PDL disables)
+    uint32_t small_flat = 32768;     // flat frames below this many entities take the thread-per-entity kernel too (ASTRE_SMALL_FLAT)
     uint32_t small_level = 32768;    // hierarchy levels below this many entities take the thread-per-entity kernel (measured: config 2, 0.159 -> 0.139 ms)
     ViewSet h_viewset;               // single-world view records, passed as a kernel parameter
     std::string err;
@@ -555,6 +556,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
         CKC(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
         ctx->coop_launch = coop != 0 && !std::getenv("ASTRE_NO_COOP");
         if (const char *m = std::getenv("ASTRE_SMALL_LEVEL")) ctx->small_level = (uint32_t)std::atol(m);
+        if (const char *m = std::getenv("ASTRE_SMALL_FLAT")) ctx->small_flat = (uint32_t)std::atol(m);
         if (std::getenv("ASTRE_NO_CONES")) ctx->use_cones = false;
         int occ_cones = 0;
         CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cones, k_hier_cones<true>, kBlockThreads, 0));
@@ -919,6 +921,16 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
             cfg.gridDim = dim3(ctx->n_cones); cfg.blockDim = dim3(kBlockThreads); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
             if (cull) CK(cudaLaunchKernelEx(&cfg, k_hier_cones<true>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
             else CK(cudaLaunchKernelEx(&cfg, k_hier_cones<false>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
+            CK_LAUNCH();
+        } else if (!ctx->has_parents && n < ctx->small_flat) {
+            // a frame this small is all latency: one entity per thread finishes in a third of the tiled kernel's first tile
+            cudaLaunchAttribute pdl;
+            pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(std::min<uint32_t>(ceil_div(n, kBlockThreads), (uint32_t)ctx->sm_count * 8)); cfg.blockDim = dim3(kBlockThreads);
+            cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, k_transform_cull_indexed, P, bp, (const uint32_t *)nullptr, 0u, n));
             CK_LAUNCH();
         } else if (!ctx->has_parents) {
             LevelTable LT{};

@@ -359,6 +359,7 @@ k_transform_cull_indexed(const FrameParams P, const __grid_constant__ BinPlan bp
     const int lane = threadIdx.x & 31;
     const bool cull = P.views_per_world != 0;
     const uint32_t n_round = (n + 31u) & ~31u;
+    cudaGridDependencySynchronize();       // (no-op unless launched as a programmatic dependent)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n;
         const uint32_t slot = active ? (slots ? slots[i] : first + i) : 0u;   // slots == nullptr: the range [first, first+n)

@@ -29,7 +29,11 @@ def run(name, scene, bytes_per_entity):
 
 for which in (sys.argv[1:] or ["config2", "config5", "config4", "dense"]):
     t0 = time.time()
-    if which == "config2":
+    if which == "config1":
+        run("config1 (10k flat, 1 view)", scenes.config1(), 108)
+    elif which.startswith("flat"):
+        run(f"config3 stream, {which[4:]} entities, 5 views", scenes.config3(int(which[4:])), 108)
+    elif which == "config2":
         run("config2 (1M, 8-level hierarchy, 1 view)", scenes.config2(), 108 + 68 * 254 / 255)
     elif which == "config5":
         run("config5 (4096 worlds x 16384, 1 view each)", scenes.config5(), 108)
