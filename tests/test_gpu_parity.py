@@ -34,12 +34,23 @@ def check_scene(oracle, scene):
     return len(o_keys)
 
 
-def test_config1_flat_10k(oracle):
+@pytest.fixture(params=["thread-per-entity", "tiled"])
+def small_flat_kernel(request, monkeypatch):
+    """Flat frames below 262,144 entities take k_transform_cull_indexed; ASTRE_SMALL_FLAT=0 sends them through the tiled
+    TMA kernel (k_frame_fused) like big frames.  Small scenes are run through BOTH."""
+    if request.param == "tiled":
+        monkeypatch.setenv("ASTRE_SMALL_FLAT", "0")
+    else:
+        monkeypatch.delenv("ASTRE_SMALL_FLAT", raising=False)
+    return request.param
+
+
+def test_config1_flat_10k(oracle, small_flat_kernel):
     assert check_scene(oracle, scenes.config1()) > 0
 
 
 @pytest.mark.parametrize("n", [1, 3, 127, 128, 129, 1023, 1024, 1025, 4099])
-def test_ragged_sizes(oracle, n):
+def test_ragged_sizes(oracle, n, small_flat_kernel):
     check_scene(oracle, scenes.config1(n))
 
 
@@ -167,7 +178,7 @@ def test_config5_worlds(oracle):
     assert check_scene(oracle, s) > 0
 
 
-def test_all_visible_multi_tile_sort(oracle):
+def test_all_visible_multi_tile_sort(oracle, small_flat_kernel):
     """Every entity inside every view: exercises compaction at full rate and a
     multi-tile sort with all eight digit passes live in the low bits."""
     s = scenes.config1(300_000)
@@ -180,7 +191,7 @@ def test_all_visible_multi_tile_sort(oracle):
     assert n_keys > 2 * s.n
 
 
-def test_edge_values_bit_exact(oracle):
+def test_edge_values_bit_exact(oracle, small_flat_kernel):
     """-0, denormals, Inf, NaN, negative and zero scale, un-normalised and zero quaternions."""
     s = scenes.config1(4096)
     specials = np.array([0.0, -0.0, 1.0, -1.0, 1e-42, -1e-42, 3e38, -3e38, np.inf, -np.inf, np.nan,
@@ -197,7 +208,7 @@ def test_edge_values_bit_exact(oracle):
     check_scene(oracle, s)
 
 
-def test_invisible_and_phase_masks(oracle):
+def test_invisible_and_phase_masks(oracle, small_flat_kernel):
     s = scenes.config3(50_000)
     s.pos = (s.pos * np.float32(0.01)).astype(np.float32)
     s.pos[:, 2] -= np.float32(30.0)
@@ -239,7 +250,7 @@ def test_basis_vectors(oracle):
         assert np.array_equal(oracle_lib.bits(a), oracle_lib.bits(b))
 
 
-def test_dirty_updates(oracle):
+def test_dirty_updates(oracle, small_flat_kernel):
     s = scenes.config1(20_000)
     with GpuContext(s.n) as ctx:
         scenes.load_into(ctx, s)
@@ -377,7 +388,7 @@ def test_interpolate(oracle):
 
 
 @pytest.mark.parametrize("graph", [False, True])
-def test_stress_moving_camera_and_dirty_sets(oracle, graph):
+def test_stress_moving_camera_and_dirty_sets(oracle, graph, small_flat_kernel):
     """Many frames on one context: the camera turns, entities move, flags flip -- every frame equals the oracle
     (shakes out stale state between frames: look-back epochs, bucket counts, counters, key buffers).  With the frame
     replayed as a CUDA graph the view records of every frame are patched into the captured launch."""
@@ -721,7 +732,7 @@ def _random_scene(rng, i):
     return s
 
 
-def test_fuzz_small_scenes(oracle):
+def test_fuzz_small_scenes(oracle, small_flat_kernel):
     """150 random small scenes (sizes around tile boundaries, 1..8 views of every kind including degenerate
     matrices, random masks / flags / bounds / parents, special values): world matrices, counts and sorted keys
     bit-exact against the oracle."""
@@ -734,7 +745,7 @@ def test_fuzz_small_scenes(oracle):
             raise AssertionError(f"scene {i} (n={s.n}, views={s.views_per_world}, hier={s.parent is not None}): {e}") from None
 
 
-def test_fuzz_batched_worlds(oracle):
+def test_fuzz_batched_worlds(oracle, small_flat_kernel):
     """Random batches of independent worlds: world sizes on and off the 128-entity warp tile (cached and
     uncached view records), 1..3 views per world, random cameras per world."""
     rng = np.random.default_rng(424242)
