@@ -222,7 +222,7 @@ __device__ __forceinline__ void publish_results(FrameResultHost *res, const Fram
                                                 const uint32_t n_counts, const bool with_counts, const CountsMirror &mirror)
 {
     if (with_counts && mirror.slot[0]) {
-        uint32_t *dst = mirror.slot[sc->epoch & 1u];
+        uint32_t *dst = (sc->epoch & 1u) ? mirror.slot[1] : mirror.slot[0];     // (a select: indexing the parameter would put it in local memory)
         for (uint32_t i = threadIdx.x; i < n_counts; i += 256u) dst[i] = counts[i];
     }
     if (!res) return;
