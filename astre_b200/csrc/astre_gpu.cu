@@ -105,7 +105,9 @@ struct astre_gpu_ctx {
     uint64_t views_version = 1, params_version = 1, levels_version = 1;
     bool capturing = false;
     uint32_t graph_vs_launches = 0;                     // fused launches of the captured frame that read the ViewSet parameter
-    cudaGraphNode_t graph_vs_node = nullptr;
+    cudaGraphNode_t graph_vs_node = nullptr, graph_vs_node_at_instantiate = nullptr;
+    const void *graph_vs_fn_at_instantiate = nullptr;
+    bool graph_update_ok = true;                        // ASTRE_GRAPH_NO_UPDATE=1: always instantiate anew (measurement)
     struct { FrameParams P; BinPlan bp; LevelTable LT; const void *fn; unsigned grid; } graph_vs_args;
     cudaStream_t graph_stream = nullptr;
     uint32_t graph_launches = 0, graph_captures = 0, graph_view_patches = 0;
@@ -558,6 +560,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
         if (const char *m = std::getenv("ASTRE_SMALL_LEVEL")) ctx->small_level = (uint32_t)std::atol(m);
         if (const char *m = std::getenv("ASTRE_SMALL_FLAT")) ctx->small_flat = (uint32_t)std::atol(m);
         if (std::getenv("ASTRE_NO_CONES")) ctx->use_cones = false;
+        if (std::getenv("ASTRE_GRAPH_NO_UPDATE")) ctx->graph_update_ok = false;
         int occ_cones = 0;
         CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cones, k_hier_cones<true>, kBlockThreads, 0));
         ctx->cone_blocks_per_sm = std::max(occ_cones, 1);
@@ -1073,9 +1076,14 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     if (s != ctx->stream && ctx->ev_views) CK(cudaStreamWaitEvent(s, ctx->ev_views, 0));
     CK(cudaEventRecord(ctx->ev_begin, s));
-    if (stage_flags & ASTRE_FRAME_GRAPH) {
+    // Until a frame has finished there is no key count to size the sort's buckets with, and the plan of the first frames is
+    // a guess that the next ones correct: those frames are launched kernel by kernel and the capture waits for the real plan.
+    // (Measured on the headline frame: an executable instantiated once with the steady plan replays in 0.3265 ms, one
+    // instantiated with the guess and updated 0.3284, one destroyed and instantiated a second time 0.335.)
+    const bool plan_settled = !fp.sort || *(volatile unsigned long long *)&ctx->h_res->key_total != ~0ull || ctx->bin_bits_override >= 0;
+    if ((stage_flags & ASTRE_FRAME_GRAPH) && plan_settled) {
         // One cudaGraphLaunch instead of 6+ launches: what matters for small frames, where the launches ARE the frame.
-        // Captured when the plan, the views, the hierarchy or the stream changed (an exec update when the topology is the same).
+        // Captured when the plan, buffers, the hierarchy or the stream changed (an exec update when the topology is the same).
         const bool stale = !ctx->graph_exec || !same_plan(fp, ctx->graph_plan) || ctx->graph_params_version != ctx->params_version ||
                            ctx->graph_levels_version != ctx->levels_version || ctx->graph_stream != s;
         bool views_changed = ctx->graph_views_version != ctx->views_version;
@@ -1110,12 +1118,29 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
             ctx->launches = launches_before;
             if (rc != ASTRE_OK) { if (g) cudaGraphDestroy(g); return rc; }
             if (ce != cudaSuccess) return fail(ctx, ASTRE_ERR_CUDA, "graph capture of the frame failed: %s", cudaGetErrorString(ce));
-            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            if (ctx->graph_obj) { cudaGraphDestroy(ctx->graph_obj); ctx->graph_obj = nullptr; }
-            const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
-            if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; return fail(ctx, ASTRE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
-            ctx->graph_obj = g;
-            if (ctx->graph_vs_launches == 1) {          // find the node of that launch
+            bool updated = false;
+            if (ctx->graph_exec && ctx->graph_update_ok) {
+                // same topology (the usual case: a new bucket width, a new entity count): update the executable in place.
+                // Its nodes keep answering to the handles of the graph it was instantiated from, which is kept.
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(ctx->graph_exec, g, &info) == cudaSuccess;
+                if (!updated) cudaGetLastError();
+            }
+            if (updated) {
+                cudaGraphDestroy(g);
+                g = ctx->graph_obj;
+                if (ctx->graph_vs_launches != 1 || ctx->graph_vs_fn_at_instantiate != ctx->graph_vs_args.fn) ctx->graph_vs_node = nullptr;
+                else ctx->graph_vs_node = ctx->graph_vs_node_at_instantiate;
+            } else {
+                if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+                if (ctx->graph_obj) { cudaGraphDestroy(ctx->graph_obj); ctx->graph_obj = nullptr; }
+                const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+                if (ie != cudaSuccess) { cudaGraphDestroy(g); ctx->graph_exec = nullptr; return fail(ctx, ASTRE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+                ctx->graph_obj = g;
+                ctx->graph_vs_node_at_instantiate = nullptr;
+                ctx->graph_vs_fn_at_instantiate = nullptr;
+            }
+            if (!updated && ctx->graph_vs_launches == 1) {          // find the node of that launch
                 size_t n_nodes = 0;
                 CK(cudaGraphGetNodes(g, nullptr, &n_nodes));
                 std::vector<cudaGraphNode_t> nodes(n_nodes);
@@ -1129,6 +1154,8 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
                     if (kp.func == ctx->graph_vs_args.fn) { ctx->graph_vs_node = nd; ++found; }
                 }
                 if (found != 1) ctx->graph_vs_node = nullptr;     // ambiguous: a change of views captures again
+                ctx->graph_vs_node_at_instantiate = ctx->graph_vs_node;
+                ctx->graph_vs_fn_at_instantiate = ctx->graph_vs_args.fn;
             }
             ctx->graph_plan = fp;
             ctx->graph_views_version = ctx->views_version;
