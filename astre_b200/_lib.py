@@ -47,6 +47,7 @@ SIGNATURES = {
     "astre_gpu_frame": (C.c_int, [_P, C.c_uint32, _P]),
     "astre_gpu_sort": (C.c_int, [_P, _P]),
     "astre_gpu_last_sort_path": (C.c_int, [_P, _U32]),
+    "astre_gpu_graph_stats": (C.c_int, [_P, _U32, _U32, _U32]),
     "astre_gpu_debug_sort_keys": (C.c_int, [_P, _U64, C.c_uint64, C.c_uint64, C.c_uint32, _U64, _U32]),
     "astre_gpu_set_counts_mirror": (C.c_int, [_P, _P, _P]),
     "astre_gpu_frame_index": (C.c_int, [_P, _U64]),

@@ -1080,7 +1080,8 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
     // a guess that the next ones correct: those frames are launched kernel by kernel and the capture waits for the real plan.
     // (Measured on the headline frame: an executable instantiated once with the steady plan replays in 0.3265 ms, one
     // instantiated with the guess and updated 0.3284, one destroyed and instantiated a second time 0.335.)
-    const bool plan_settled = !fp.sort || *(volatile unsigned long long *)&ctx->h_res->key_total != ~0ull || ctx->bin_bits_override >= 0;
+    const bool plan_settled = !fp.sort || *(volatile unsigned long long *)&ctx->h_res->key_total != ~0ull || ctx->bin_bits_override >= 0 ||
+                              std::getenv("ASTRE_GRAPH_EAGER_CAPTURE") != nullptr;
     if ((stage_flags & ASTRE_FRAME_GRAPH) && plan_settled) {
         // One cudaGraphLaunch instead of 6+ launches: what matters for small frames, where the launches ARE the frame.
         // Captured when the plan, buffers, the hierarchy or the stream changed (an exec update when the topology is the same).
@@ -1374,6 +1375,15 @@ int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t
     ctx->frame_done = false;                                 // the key buffers no longer hold a frame's list
     ctx->results_cached = false;
     ctx->sort_pending = false;
+    return ASTRE_OK;
+}
+
+int astre_gpu_graph_stats(const astre_gpu_ctx *ctx, uint32_t *captures, uint32_t *view_patches, uint32_t *bucket_bits)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (captures) *captures = ctx->graph_captures;
+    if (view_patches) *view_patches = ctx->graph_view_patches;
+    if (bucket_bits) *bucket_bits = ctx->pending_bins.bits;
     return ASTRE_OK;
 }
 

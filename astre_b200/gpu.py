@@ -149,6 +149,12 @@ class GpuContext:
                                                         _ptr(out, C.c_uint64), C.byref(path)))
         return out, int(path.value)
 
+    def graph_stats(self):
+        """(captures or exec updates, view-record patches, bucket-digit bits of the last plan) of ASTRE_FRAME_GRAPH frames."""
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.astre_gpu_graph_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
     def last_sort_path(self):
         """0 = no sort ran, 1 = bucket sort, 2 = LSD radix fallback (decided on the device)."""
         v = C.c_uint32(0)

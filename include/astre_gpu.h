@@ -179,6 +179,9 @@ ASTRE_API int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream);
  * Appendix B): the reference has no draw-order sort (deferred_shading.cpp:115,151 walk a hash map).
  * Synchronises. */
 ASTRE_API int astre_gpu_last_sort_path(astre_gpu_ctx *ctx, uint32_t *path);
+/* Diagnostics of ASTRE_FRAME_GRAPH: how often the frame was captured (or its executable updated), how often only the
+ * view records were patched into it, and the bucket-digit width of the last frame's sort plan. */
+ASTRE_API int astre_gpu_graph_stats(const astre_gpu_ctx *ctx, uint32_t *captures, uint32_t *view_patches, uint32_t *bucket_bits);
 /* Test hook of the spec-defined key sort (no reference counterpart): sorts n UNIQUE 64-bit keys whose varying bits lie
  * inside live_mask with a bucket digit of bin_bits bits, through exactly the kernels a frame uses (bucket path or,
  * chosen on the device, the LSD fallback); *path_out as astre_gpu_last_sort_path.  Invalidates the last frame's
