@@ -411,9 +411,11 @@ class Bench:
         keys_np, vis_np = keys_h.numpy().view(np.uint64), vis_h.numpy()
         cnt_np = np.zeros(max(self.n_counts, 1), np.uint32)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if n <= 2_000_000:
+            steps = max(steps, 20)          # sub-millisecond steps: three of them would be all noise
 
         def timed(fn, reps):
-            for _ in range(2):
+            for _ in range(3):
                 fn()
             self.barrier()
             e0.record(self.stream)
