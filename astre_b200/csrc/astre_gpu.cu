@@ -92,7 +92,9 @@ struct astre_gpu_ctx {
     uint32_t *d_head_counts = nullptr;   // run heads per CTA of k_run_count, then their exclusive scan (+ total)
     uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
     uint32_t epoch = 0;                  // host mirror of SortControl::epoch (one step per frame)
-    uint32_t last_want_bits = 0;         // bucket-digit width of the last plan (hysteresis)
+    uint32_t last_want_bits = 0;         // bucket-digit width of the last plan by key count (hysteresis)
+    int bits_bias = 0;                   // correction of that width from the buckets' measured crowding
+    bool bits_feedback = true;           // ASTRE_SORT_NO_FEEDBACK=1 switches the correction off (measurement)
 
     // ASTRE_FRAME_GRAPH: the frame's launches as one instantiated CUDA graph
     cudaGraphExec_t graph_exec = nullptr;
@@ -526,6 +528,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     ctx->h_res->key_total = ~0ull;                                   // no frame has finished yet
     CKC(cudaHostGetDevicePointer(&ctx->d_res, ctx->h_res, 0));
     if (std::getenv("ASTRE_SORT_FORCE_LSD")) ctx->force_lsd = 1u;
+    if (std::getenv("ASTRE_SORT_NO_FEEDBACK")) ctx->bits_feedback = false;
     if (const char *m = std::getenv("ASTRE_SORT_BIN_BITS")) ctx->bin_bits_override = std::atoi(m);
     {
         int occ_sort = 0;
@@ -1062,7 +1065,33 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         uint32_t want = kMinBinBits;
         while (want < ctx->cap_bin_bits && (1ull << want) * 8ull < expect) ++want;
         if (ctx->last_want_bits && want + 1 >= ctx->last_want_bits && want <= ctx->last_want_bits + 1) want = ctx->last_want_bits;
+        if (want != ctx->last_want_bits) ctx->bits_bias = 0;
         ctx->last_want_bits = want;
+        // Feedback from the buckets themselves: sum(m^2) / n is the mean length of a key's rank loop.  Keys rarely fill the
+        // digit's value range evenly (two of eight view values hold 99 % of the headline frame's keys: mean 21; depths
+        // cluster: mean 190 on a dense scene), so the width is widened while that mean is LONG and narrowed again when it is
+        // very short -- one bit per finished frame that ran with the current width.  Only long: a wider table makes the
+        // rank kernel cheaper but the cull kernel's REDs dearer (a table that does not stay hot in L2 while 1.8 GB stream
+        // through it turns them into DRAM read-modify-writes; measured on the headline frame: 2^19 instead of 2^17 bins
+        // = rank -2 us, cull kernel +6 us).
+        {
+            const FrameResultHost &R = *ctx->h_res;
+            const unsigned long long kt = *(volatile unsigned long long *)&R.key_total;
+            const uint32_t nb = *(volatile uint32_t *)&R.n_bins;
+            const unsigned long long sq = *(volatile unsigned long long *)&R.sum_sq;
+            const uint32_t cur = std::min<uint32_t>(std::max<int>((int)want + ctx->bits_bias, (int)kMinBinBits), ctx->cap_bin_bits);
+            // (only feedback from a frame that ran with the CURRENT width counts: one step, then wait for its effect)
+            if (kt != ~0ull && kt > 1024 && nb == (1u << cur) && ctx->bits_feedback) {
+                const unsigned long long mean = sq / kt;
+                // ... and only while the wider table would still be hot: ~1.2 M entities stream through L2 between two
+                // evictions of a line, and a line holds 32 bins, so at least ~8 REDs per line and window means
+                // bins <= 4.7 M x keys / entities (dense 4 M-entity scene: 4.4 M bins; headline frame: 0.2 M; 64 M-entity frame: 0.2 M)
+                const unsigned long long hot_limit = kt * 4700000ull / std::max<uint32_t>(n, 1u);
+                if (mean > 48 && cur < ctx->cap_bin_bits && (2ull << cur) <= hot_limit) ++ctx->bits_bias;
+                else if (mean < 3 && cur > kMinBinBits && ctx->bits_bias > -3) --ctx->bits_bias;
+            }
+            want = std::min<uint32_t>(std::max<int>((int)want + ctx->bits_bias, (int)kMinBinBits), ctx->cap_bin_bits);
+        }
         if (ctx->bin_bits_override >= 0) want = std::max<uint32_t>(2u, std::min<uint32_t>((uint32_t)ctx->bin_bits_override, ctx->cap_bin_bits));
         fp.bp = make_bin_plan(live, want);
     }

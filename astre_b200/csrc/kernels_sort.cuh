@@ -64,7 +64,7 @@ struct SortControl {
     uint32_t result_buf;                 // key buffer (0 / 1) that holds the sorted list
     uint32_t lsd_barrier;                // arrivals at the fallback's grid barrier
     uint32_t path;                       // SortPath of the last sort
-    uint32_t pad;
+    uint32_t n_bins;                     // bucket sort: bins of this frame (k_bin_scan)
     unsigned long long scan_state[kMaxScanTiles];   // look-back words of the bin scan
 };
 
@@ -207,7 +207,9 @@ struct FrameResultHost {
     uint32_t n_counts;                                  // counts / offsets mirrored below (0: too many, copy them from the device)
     uint32_t counts[kInlineCounts];
     unsigned long long offsets[kInlineCounts + 1];
-    uint32_t list_n, list_pad;                          // k_gather_list: length of the list mirrored below, or kNoInlineList
+    uint32_t list_n;                                    // k_gather_list: length of the list mirrored below, or kNoInlineList
+    uint32_t n_bins;                                    // bucket sort feedback: bins of this frame and the sum of squared bucket
+    unsigned long long sum_sq;                          // sizes (sum_sq / key_total = mean length of a key's rank loop)
     unsigned long long list_keys[kInlineList];
     float4 list_world[kInlineList * 4];
 };
@@ -231,6 +233,8 @@ __device__ __forceinline__ void publish_results(FrameResultHost *res, const Fram
         res->overflow = ctl->overflow;
         res->result_buf = sc->result_buf;
         res->path = sc->path;
+        res->n_bins = sc->n_bins;
+        res->sum_sq = sc->sum_sq;
         res->list_n = kNoInlineList;                    // k_gather_list, if the frame has one, runs after this
     }
     if (with_counts) {
@@ -347,7 +351,7 @@ k_bin_scan(uint32_t *__restrict__ bins, const uint32_t n_bins, SortControl *sc, 
     for (int i = 0; i < 4; ++i)
         if (st[i + 1] - st[i] <= kMaxBucket)
             for (uint32_t cc = st[i] / kChunkKeys + 1u; cc * kChunkKeys <= st[i + 1]; ++cc) chunk_first[cc] = e0 + i + 1u;
-    if (tile == 0 && threadIdx.x == 0) chunk_first[0] = 0u;
+    if (tile == 0 && threadIdx.x == 0) { chunk_first[0] = 0u; sc->n_bins = n_bins; }
 }
 
 // key -> its bucket; the position inside the bucket comes from an atomic cursor (unordered).

@@ -341,13 +341,13 @@ class Bench:
             self.exchange.finish()
         self.barrier()
         # The frame graph is captured once a finished frame has told the host how many keys to size the sort's buckets for
-        # (astre_gpu.cu: plan_settled).  Frames enqueued back to back before that ran kernel by kernel; two more untimed
-        # steps after the synchronisation make sure the capture does not land inside the timed region.
-        for _ in range(2):
+        # (astre_gpu.cu: plan_settled).  Frames enqueued back to back before that ran kernel by kernel; four more untimed
+        # steps, each followed by a synchronisation, make sure the capture does not land inside the timed region.
+        for _ in range(4):                 # (the bucket width also settles over the first finished frames: one bit per frame)
             self.step()
-        if self.exchange:
-            self.exchange.finish()
-        self.barrier()
+            if self.exchange:
+                self.exchange.finish()
+            self.barrier()
         launches0 = self.ctx.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()

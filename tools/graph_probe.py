@@ -20,7 +20,7 @@ def timed(ctx, flags, steps=30):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(5):
         ctx.frame(flags)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(steps):
         ctx.frame(flags)
