@@ -52,6 +52,8 @@ SIGNATURES = {
     "astre_gpu_set_counts_mirror": (C.c_int, [_P, _P, _P]),
     "astre_gpu_frame_index": (C.c_int, [_P, _U64]),
     "astre_gpu_global_offsets_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "astre_gpu_debug_guard_check": (C.c_int64, []),
+    "astre_gpu_debug_guard_selftest": (C.c_int64, []),
     "astre_gpu_sync": (C.c_int, [_P]),
     "astre_gpu_set_stream": (C.c_int, [_P, _P]),
     "astre_gpu_launch_count": (C.c_uint64, [_P]),

@@ -7,8 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/astre_gpu.h"
@@ -27,6 +29,78 @@ static_assert(sizeof(astre_mesh_bounds) == sizeof(BoundsDev), "bounds records mu
 namespace {
 
 thread_local std::string g_create_error;
+
+// ---- guarded device allocations (ASTRE_GUARD=1; the GPU tests run with it) ----------------------------------------
+// Every device buffer gets a 4 KB canary on both sides; astre_gpu_debug_guard_check() and every dev_free() look at them.
+// A store that leaves its buffer by less than a page would otherwise land in a neighbouring allocation unnoticed.
+constexpr size_t kGuardBytes = 4096;
+constexpr unsigned char kGuardFill = 0xA5;
+std::mutex g_guard_mutex;
+std::unordered_map<void *, size_t> g_guarded;      // user pointer -> user bytes
+uint64_t g_guard_violations = 0;
+
+bool guard_enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("ASTRE_GUARD"); return e && *e && *e != '0'; }();
+    return on;
+}
+
+// Bytes of the two canaries of one allocation that no longer hold the fill value.
+uint64_t guard_damage(void *user, size_t bytes)
+{
+    std::vector<unsigned char> h(2 * kGuardBytes);
+    unsigned char *base = static_cast<unsigned char *>(user) - kGuardBytes;
+    if (cudaMemcpy(h.data(), base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(h.data() + kGuardBytes, static_cast<unsigned char *>(user) + bytes, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 1;
+    uint64_t bad = 0;
+    for (size_t i = 0; i < h.size(); ++i)
+        if (h[i] != kGuardFill) {
+            if (!bad)
+                std::fprintf(stderr, "astre_gpu: guard of a %zu-byte device buffer overwritten %s it (offset %zd)\n", bytes,
+                             i < kGuardBytes ? "before" : "after", i < kGuardBytes ? (ptrdiff_t)i - (ptrdiff_t)kGuardBytes : (ptrdiff_t)(i - kGuardBytes));
+            ++bad;
+        }
+    return bad;
+}
+
+cudaError_t dev_alloc_bytes(void **p, size_t bytes)
+{
+    if (!guard_enabled()) return cudaMalloc(p, bytes);
+    const size_t padded = (bytes + 255) / 256 * 256;      // the rear canary starts where the (rounded) buffer ends
+    unsigned char *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, padded + 2 * kGuardBytes);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemset(base, kGuardFill, kGuardBytes)) != cudaSuccess ||
+        (e = cudaMemset(base + kGuardBytes + bytes, kGuardFill, padded - bytes + kGuardBytes)) != cudaSuccess) {
+        cudaFree(base);
+        return e;
+    }
+    *p = base + kGuardBytes;
+    std::lock_guard<std::mutex> lock(g_guard_mutex);
+    g_guarded[*p] = bytes;
+    return cudaSuccess;
+}
+
+template <class T>
+cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc_bytes(reinterpret_cast<void **>(p), bytes); }
+
+cudaError_t dev_free(void *p)
+{
+    if (!p || !guard_enabled()) return cudaFree(p);
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mutex);
+        auto it = g_guarded.find(p);
+        if (it == g_guarded.end()) return cudaFree(p);
+        bytes = it->second;
+        g_guarded.erase(it);
+    }
+    cudaDeviceSynchronize();
+    const uint64_t bad = guard_damage(p, bytes);
+    if (bad) { std::lock_guard<std::mutex> lock(g_guard_mutex); g_guard_violations += bad; }
+    return cudaFree(static_cast<unsigned char *>(p) - kGuardBytes);
+}
 
 struct Level {
     uint32_t first = 0, count = 0;  // range [first, first+count) when contiguous
@@ -374,9 +448,9 @@ int rebuild_levels(astre_gpu_ctx *ctx)
                 }
             }
             if (ctx->cap_cones < ranges.size()) {
-                if (ctx->d_cones) cudaFree(ctx->d_cones);
+                if (ctx->d_cones) dev_free(ctx->d_cones);
                 ctx->d_cones = nullptr;
-                CK(cudaMalloc(&ctx->d_cones, ranges.size() * sizeof(uint2)));
+                CK(dev_alloc(&ctx->d_cones, ranges.size() * sizeof(uint2)));
                 ctx->cap_cones = ranges.size();
             }
             CK(cudaMemcpyAsync(ctx->d_cones, ranges.data(), ranges.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
@@ -386,9 +460,9 @@ int rebuild_levels(astre_gpu_ctx *ctx)
     }
     if (any_list) {
         if (ctx->cap_level_slots < n) {
-            if (ctx->d_level_slots) cudaFree(ctx->d_level_slots);
+            if (ctx->d_level_slots) dev_free(ctx->d_level_slots);
             ctx->d_level_slots = nullptr;
-            CK(cudaMalloc(&ctx->d_level_slots, (size_t)ctx->cap_entities * sizeof(uint32_t)));
+            CK(dev_alloc(&ctx->d_level_slots, (size_t)ctx->cap_entities * sizeof(uint32_t)));
             ctx->cap_level_slots = ctx->cap_entities;
         }
         CK(cudaMemcpyAsync(ctx->d_level_slots, order.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -431,7 +505,7 @@ int ensure_stage(astre_gpu_ctx *ctx)
 {
     if (ctx->d_stage) return ASTRE_OK;
     ctx->stage_entities = std::min<uint32_t>(std::max<uint32_t>(ctx->max_entities, 1u), 1u << 19);
-    CK(cudaMalloc(&ctx->d_stage, (size_t)ctx->stage_entities * 64 * 2));
+    CK(dev_alloc(&ctx->d_stage, (size_t)ctx->stage_entities * 64 * 2));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
@@ -494,35 +568,35 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     const size_t cap = ctx->cap_entities;
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    CKC(cudaMalloc(&ctx->d_tiles, ctx->tile_words() * sizeof(float)));
+    CKC(dev_alloc(&ctx->d_tiles, ctx->tile_words() * sizeof(float)));
     CKC(cudaMemset(ctx->d_tiles, 0, ctx->tile_words() * sizeof(float)));
     k_init_tiles<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_tiles, ctx->cap_entities);
     CKC(cudaGetLastError());
-    CKC(cudaMalloc(&ctx->d_world, cap * 4 * sizeof(float4)));
+    CKC(dev_alloc(&ctx->d_world, cap * 4 * sizeof(float4)));
     ctx->cap_meshes = 16;
-    CKC(cudaMalloc(&ctx->d_bounds, ctx->cap_meshes * sizeof(BoundsDev)));
+    CKC(dev_alloc(&ctx->d_bounds, ctx->cap_meshes * sizeof(BoundsDev)));
     CKC(cudaMemset(ctx->d_bounds, 0, ctx->cap_meshes * sizeof(BoundsDev)));
     ctx->cap_view_records = std::max<uint32_t>(max_views, 1u);
-    CKC(cudaMalloc(&ctx->d_views, ctx->cap_view_records * sizeof(ViewDev)));
+    CKC(dev_alloc(&ctx->d_views, ctx->cap_view_records * sizeof(ViewDev)));
     CKC(cudaMemset(ctx->d_views, 0, ctx->cap_view_records * sizeof(ViewDev)));
-    CKC(cudaMalloc(&ctx->d_keys[0], ctx->max_keys * sizeof(unsigned long long)));
-    CKC(cudaMalloc(&ctx->d_keys[1], ctx->max_keys * sizeof(unsigned long long)));
+    CKC(dev_alloc(&ctx->d_keys[0], ctx->max_keys * sizeof(unsigned long long)));
+    CKC(dev_alloc(&ctx->d_keys[1], ctx->max_keys * sizeof(unsigned long long)));
     ctx->cap_counts = std::max<uint32_t>(max_views, 1u);
-    CKC(cudaMalloc(&ctx->d_counts, ctx->cap_counts * sizeof(uint32_t)));
-    CKC(cudaMalloc(&ctx->d_offsets, ((size_t)ctx->cap_counts + 1) * sizeof(unsigned long long)));
-    CKC(cudaMalloc(&ctx->d_ctl, sizeof(FrameControl)));
+    CKC(dev_alloc(&ctx->d_counts, ctx->cap_counts * sizeof(uint32_t)));
+    CKC(dev_alloc(&ctx->d_offsets, ((size_t)ctx->cap_counts + 1) * sizeof(unsigned long long)));
+    CKC(dev_alloc(&ctx->d_ctl, sizeof(FrameControl)));
     CKC(cudaMemset(ctx->d_ctl, 0, sizeof(FrameControl)));
-    CKC(cudaMalloc(&ctx->d_sc, sizeof(SortControl)));
+    CKC(dev_alloc(&ctx->d_sc, sizeof(SortControl)));
     CKC(cudaMemset(ctx->d_sc, 0, sizeof(SortControl)));
     const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
-    CKC(cudaMalloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
+    CKC(dev_alloc(&ctx->d_lookback, n_sort_tiles * 256 * sizeof(unsigned long long)));
     CKC(cudaMemset(ctx->d_lookback, 0, n_sort_tiles * 256 * sizeof(unsigned long long)));
     if (const char *m = std::getenv("ASTRE_CLAIM_GROUPS")) ctx->claim_groups = (uint32_t)std::max(std::atoi(m), 0);
     // key sort: buckets of ~4-8 keys -> up to max_keys / 4 bins (between 2^8 and 2^22)
     ctx->cap_bin_bits = kMinBinBits;
     while (ctx->cap_bin_bits < kMaxBinBits && (1ull << ctx->cap_bin_bits) * 4ull < ctx->max_keys) ++ctx->cap_bin_bits;
-    CKC(cudaMalloc(&ctx->d_bins, (size_t)(1u << ctx->cap_bin_bits) * sizeof(uint32_t)));
-    CKC(cudaMalloc(&ctx->d_chunk_first, (size_t)(ctx->max_keys / kChunkKeys + 2) * sizeof(uint32_t)));
+    CKC(dev_alloc(&ctx->d_bins, (size_t)(1u << ctx->cap_bin_bits) * sizeof(uint32_t)));
+    CKC(dev_alloc(&ctx->d_chunk_first, (size_t)(ctx->max_keys / kChunkKeys + 2) * sizeof(uint32_t)));
     CKC(cudaHostAlloc(&ctx->h_res, sizeof(FrameResultHost), cudaHostAllocMapped));
     std::memset(ctx->h_res, 0, sizeof(FrameResultHost));
     ctx->h_res->key_total = ~0ull;                                   // no frame has finished yet
@@ -586,9 +660,10 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
                      ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_cones, ctx->d_bins, ctx->d_chunk_first, ctx->d_heads,
                      ctx->d_head_counts,
-                     ctx->d_publish[0], ctx->d_publish[1], ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
+                     ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) dev_free(p);
+    for (unsigned char *p : ctx->d_publish) if (p) cudaFree(p);
     for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1, ctx->ev_views };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -753,9 +828,9 @@ int astre_gpu_set_mesh_bounds(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre
     CK(cudaSetDevice(ctx->device));
     if (n_meshes > ctx->cap_meshes) {
         CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaFree(ctx->d_bounds));
+        CK(dev_free(ctx->d_bounds));
         ctx->d_bounds = nullptr;
-        CK(cudaMalloc(&ctx->d_bounds, (size_t)n_meshes * sizeof(BoundsDev)));
+        CK(dev_alloc(&ctx->d_bounds, (size_t)n_meshes * sizeof(BoundsDev)));
         ctx->cap_meshes = n_meshes;
     }
     if (n_meshes) {
@@ -791,15 +866,15 @@ int astre_gpu_set_world_views(astre_gpu_ctx *ctx, uint32_t n_worlds, uint32_t en
     if (ctx->last_stream && ctx->last_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_stream));   // frames enqueued on a caller's stream
     if (reallocated) CK(cudaStreamSynchronize(ctx->stream));
     if (n_rec > ctx->cap_view_records) {
-        CK(cudaFree(ctx->d_views)); ctx->d_views = nullptr;
-        CK(cudaMalloc(&ctx->d_views, n_rec * sizeof(ViewDev)));
+        CK(dev_free(ctx->d_views)); ctx->d_views = nullptr;
+        CK(dev_alloc(&ctx->d_views, n_rec * sizeof(ViewDev)));
         ctx->cap_view_records = (uint32_t)n_rec;
     }
     if (n_rec > ctx->cap_counts) {
-        CK(cudaFree(ctx->d_counts)); ctx->d_counts = nullptr;
-        CK(cudaFree(ctx->d_offsets)); ctx->d_offsets = nullptr;
-        CK(cudaMalloc(&ctx->d_counts, n_rec * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_offsets, (n_rec + 1) * sizeof(unsigned long long)));
+        CK(dev_free(ctx->d_counts)); ctx->d_counts = nullptr;
+        CK(dev_free(ctx->d_offsets)); ctx->d_offsets = nullptr;
+        CK(dev_alloc(&ctx->d_counts, n_rec * sizeof(uint32_t)));
+        CK(dev_alloc(&ctx->d_offsets, (n_rec + 1) * sizeof(unsigned long long)));
         ctx->cap_counts = (uint32_t)n_rec;
     }
     std::vector<astre_host::ViewHost> recs(n_rec);
@@ -1096,10 +1171,10 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
         fp.bp = make_bin_plan(live, want);
     }
     if ((stage_flags & ASTRE_FRAME_BASIS) && !ctx->d_basis)
-        CK(cudaMalloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
+        CK(dev_alloc(&ctx->d_basis, (size_t)ctx->cap_entities * 9 * sizeof(float)));
     if ((stage_flags & ASTRE_FRAME_GATHER) && !ctx->d_gather) {          // room for a typical list; longer ones are gathered on read
         ctx->cap_gather = std::min<uint64_t>(ctx->max_keys, 1ull << 20);
-        CK(cudaMalloc(&ctx->d_gather, ctx->cap_gather * 64));
+        CK(dev_alloc(&ctx->d_gather, ctx->cap_gather * 64));
         ++ctx->params_version;
     }
 
@@ -1275,7 +1350,7 @@ int astre_gpu_snapshot_trs(astre_gpu_ctx *ctx, void *stream)
     if (!ctx) return ASTRE_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    if (!ctx->d_prev) CK(cudaMalloc(&ctx->d_prev, ctx->tile_words() * sizeof(float)));
+    if (!ctx->d_prev) CK(dev_alloc(&ctx->d_prev, ctx->tile_words() * sizeof(float)));
     CK(cudaMemcpyAsync(ctx->d_prev, ctx->d_tiles, ctx->tile_words() * sizeof(float), cudaMemcpyDeviceToDevice, s));
     ctx->n_prev = ctx->n_entities;
     return ASTRE_OK;
@@ -1311,8 +1386,8 @@ int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, 
     const uint32_t n_ctas = (uint32_t)ctx->sm_count * 8u;
     if (!ctx->d_heads) {
         ctx->cap_heads = (uint32_t)std::min<uint64_t>(ctx->max_keys, 1u << 22);
-        CK(cudaMalloc(&ctx->d_heads, (size_t)ctx->cap_heads * sizeof(RunHead)));
-        CK(cudaMalloc(&ctx->d_head_counts, ((size_t)n_ctas + 1) * sizeof(uint32_t)));
+        CK(dev_alloc(&ctx->d_heads, (size_t)ctx->cap_heads * sizeof(RunHead)));
+        CK(dev_alloc(&ctx->d_head_counts, ((size_t)n_ctas + 1) * sizeof(uint32_t)));
     }
     cudaStream_t s = ctx->last_stream;
     const uint32_t class_shift = 40u - ctx->world_bits;   // below it: depth and slot
@@ -1405,6 +1480,37 @@ int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t
     ctx->results_cached = false;
     ctx->sort_pending = false;
     return ASTRE_OK;
+}
+
+int64_t astre_gpu_debug_guard_check(void)
+{
+    if (!guard_enabled()) return -1;
+    cudaDeviceSynchronize();
+    std::vector<std::pair<void *, size_t>> live;
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mutex);
+        live.assign(g_guarded.begin(), g_guarded.end());
+    }
+    uint64_t bad = 0;
+    for (const auto &a : live) bad += guard_damage(a.first, a.second);
+    std::lock_guard<std::mutex> lock(g_guard_mutex);
+    return (int64_t)(g_guard_violations + bad);
+}
+
+int64_t astre_gpu_debug_guard_selftest(void)
+{
+    if (!guard_enabled()) return -1;
+    unsigned char *p = nullptr;
+    if (dev_alloc(&p, 1000) != cudaSuccess) return -2;
+    cudaMemset(p + 998, 0, 5);           // two bytes inside, three past the end
+    cudaMemset(p - 1, 0, 1);             // one before the start
+    const uint64_t bad = guard_damage(p, 1000);
+    {
+        std::lock_guard<std::mutex> lock(g_guard_mutex);
+        g_guarded.erase(p);
+    }
+    cudaFree(p - kGuardBytes);
+    return (int64_t)bad;
 }
 
 int astre_gpu_graph_stats(const astre_gpu_ctx *ctx, uint32_t *captures, uint32_t *view_patches, uint32_t *bucket_bits)
@@ -1527,9 +1633,9 @@ int astre_gpu_read_visible_world(astre_gpu_ctx *ctx, uint64_t first_key, uint64_
                                           (unsigned long long)first_key, (unsigned long long)(first_key + n), (unsigned long long)have);
     if (!n) return ASTRE_OK;
     if (ctx->cap_gather < n) {
-        if (ctx->d_gather) CK(cudaFree(ctx->d_gather));
+        if (ctx->d_gather) CK(dev_free(ctx->d_gather));
         ctx->d_gather = nullptr;
-        CK(cudaMalloc(&ctx->d_gather, n * 64));
+        CK(dev_alloc(&ctx->d_gather, n * 64));
         ctx->cap_gather = n;
         ++ctx->params_version;                  // a captured frame graph has the old buffer baked in
     }
@@ -1567,9 +1673,9 @@ int astre_gpu_read_draw_list(astre_gpu_ctx *ctx, uint64_t *keys, float *world16,
     }
     if (world16) {
         if (ctx->cap_gather < n) {
-            if (ctx->d_gather) CK(cudaFree(ctx->d_gather));
+            if (ctx->d_gather) CK(dev_free(ctx->d_gather));
             ctx->d_gather = nullptr;
-            CK(cudaMalloc(&ctx->d_gather, n * 64));
+            CK(dev_alloc(&ctx->d_gather, n * 64));
             ctx->cap_gather = n;
             ++ctx->params_version;              // a captured frame graph has the old buffer baked in
         }
@@ -1622,14 +1728,14 @@ int ensure_publish(astre_gpu_ctx *ctx, uint32_t parity)
     if (ctx->d_publish[parity]) return ASTRE_OK;
     void *p = nullptr;
     const PublishLayout P = publish_layout(ctx->max_keys);
-    CK(cudaMalloc(&p, P.bytes));
+    CK(cudaMalloc(&p, P.bytes));      // not guarded: peers map this allocation by its base address (CUDA IPC)
     CK(cudaMemset(static_cast<unsigned char *>(p) + P.header_off, 0, sizeof(PublishHeader)));      // flags start at epoch 0
     ctx->d_publish[parity] = static_cast<unsigned char *>(p);
     if (!ctx->d_merge_error) {      // allocated here, not inside the per-frame calls: those must never block on the device
-        CK(cudaMalloc(&ctx->d_merge_error, sizeof(uint32_t)));
+        CK(dev_alloc(&ctx->d_merge_error, sizeof(uint32_t)));
         CK(cudaMemset(ctx->d_merge_error, 0, sizeof(uint32_t)));
     }
-    if (!ctx->d_mdims) CK(cudaMalloc(&ctx->d_mdims, sizeof(MergeDims)));
+    if (!ctx->d_mdims) CK(dev_alloc(&ctx->d_mdims, sizeof(MergeDims)));
     return ASTRE_OK;
 }
 
@@ -1661,21 +1767,21 @@ int fill_lists(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_lists, const uint64
 int ensure_merge_buffers(astre_gpu_ctx *ctx, uint64_t out_count, uint32_t n_samples, bool exact)
 {
     if (ctx->cap_merged < out_count || !ctx->d_merged_keys) {
-        if (ctx->d_merged_keys) CK(cudaFree(ctx->d_merged_keys));
-        if (ctx->d_merged_src) CK(cudaFree(ctx->d_merged_src));
+        if (ctx->d_merged_keys) CK(dev_free(ctx->d_merged_keys));
+        if (ctx->d_merged_src) CK(dev_free(ctx->d_merged_src));
         ctx->d_merged_keys = nullptr; ctx->d_merged_src = nullptr; ctx->cap_merged = 0;
         const uint64_t cap = std::max<uint64_t>(exact ? out_count : out_count + out_count / 4, 1024);
-        CK(cudaMalloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
-        CK(cudaMalloc(&ctx->d_merged_src, cap));
+        CK(dev_alloc(&ctx->d_merged_keys, cap * sizeof(unsigned long long)));
+        CK(dev_alloc(&ctx->d_merged_src, cap));
         ctx->cap_merged = cap;
     }
     if (ctx->cap_merge_tiles < n_samples + 1 || !ctx->d_splits) {
-        if (ctx->d_splits) CK(cudaFree(ctx->d_splits));
-        if (ctx->d_tile_start) CK(cudaFree(ctx->d_tile_start));
+        if (ctx->d_splits) CK(dev_free(ctx->d_splits));
+        if (ctx->d_tile_start) CK(dev_free(ctx->d_tile_start));
         ctx->d_splits = nullptr; ctx->d_tile_start = nullptr; ctx->cap_merge_tiles = 0;
         const uint32_t cap = exact ? n_samples + 1 : n_samples + n_samples / 4 + 64;
-        CK(cudaMalloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
+        CK(dev_alloc(&ctx->d_splits, (size_t)cap * kMaxLists * sizeof(uint32_t)));
+        CK(dev_alloc(&ctx->d_tile_start, (size_t)cap * sizeof(uint32_t)));
         ctx->cap_merge_tiles = cap;
     }
     return ASTRE_OK;
@@ -1812,10 +1918,10 @@ int astre_gpu_merge_lists(astre_gpu_ctx *ctx, uint32_t n_lists, const void *cons
     cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
     const uint32_t n_samples = L.d.sample_base[n_lists];
     if (ctx->cap_msamples < n_samples || !ctx->d_mcuts) {
-        if (ctx->d_mcuts) CK(cudaFree(ctx->d_mcuts));
+        if (ctx->d_mcuts) CK(dev_free(ctx->d_mcuts));
         ctx->d_mcuts = nullptr; ctx->cap_msamples = 0;
         const uint32_t cap = n_samples + n_samples / 4 + 64;
-        CK(cudaMalloc(&ctx->d_mcuts, (size_t)cap * kMaxLists * 4));
+        CK(dev_alloc(&ctx->d_mcuts, (size_t)cap * kMaxLists * 4));
         ctx->cap_msamples = cap;
     }
     if (int rc = merge_begin(ctx, s)) return rc;
@@ -1905,7 +2011,7 @@ static int lists_from_publish(astre_gpu_ctx *ctx, MergeLists &L, uint32_t n_list
         L.samples[t] = reinterpret_cast<const unsigned long long *>(base + P.samples_off);
         L.cuts[t] = reinterpret_cast<const uint32_t *>(base + P.cuts_off);
     }
-    if (!ctx->d_mdims) CK(cudaMalloc(&ctx->d_mdims, sizeof(MergeDims)));
+    if (!ctx->d_mdims) CK(dev_alloc(&ctx->d_mdims, sizeof(MergeDims)));
     L.dev_dims = ctx->d_mdims;
     return ASTRE_OK;
 }

@@ -50,6 +50,10 @@ class GpuContext:
         if getattr(self, "_h", None):
             self._lib.astre_gpu_destroy(self._h)
             self._h = None
+            # ASTRE_GUARD=1 (the GPU tests): a kernel that stored outside one of the library's buffers fails here
+            damaged = self._lib.astre_gpu_debug_guard_check()
+            if damaged > 0:
+                raise RuntimeError(f"astre_gpu: {damaged} guard bytes around device buffers were overwritten")
 
     def __enter__(self):
         return self

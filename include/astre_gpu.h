@@ -188,6 +188,13 @@ ASTRE_API int astre_gpu_graph_stats(const astre_gpu_ctx *ctx, uint32_t *captures
  * results.  Lets tests drive the sort with key sets no scene produces. */
 ASTRE_API int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t n, uint64_t live_mask,
                                         uint32_t bin_bits, uint64_t *sorted_out, uint32_t *path_out);
+/* Test hook: with ASTRE_GUARD=1 in the environment every device buffer of the library carries a 4 KB canary on both
+ * sides.  Checks the canaries of all live buffers (synchronises the device) and returns the number of canary bytes found
+ * overwritten so far, including those seen when buffers were freed; -1 when guards are off.  No reference counterpart. */
+ASTRE_API int64_t astre_gpu_debug_guard_check(void);
+/* Overruns a scratch buffer on purpose (three bytes past its end, one before its start) and returns the damage the
+ * detector reports for it (4); does not count towards astre_gpu_debug_guard_check.  -1 when guards are off. */
+ASTRE_API int64_t astre_gpu_debug_guard_selftest(void);
 ASTRE_API int astre_gpu_sync(astre_gpu_ctx *ctx);
 /* Makes every later call on ctx (mirror updates, frames with stream == NULL,
  * read-backs) enqueue on the caller's cudaStream_t instead of the context's own

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Every device buffer of the library gets canaries while the tests run (astre_gpu_debug_guard_check; GpuContext.close
+# raises when a kernel stored outside its buffer).  Must be set before the library reads it.
+os.environ.setdefault("ASTRE_GUARD", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

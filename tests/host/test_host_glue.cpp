@@ -487,6 +487,9 @@ int main(int argc, char **argv)
         test_frame_interpolation(5000);
         if (ref::load(argv[0])) test_against_reference_build(20000);
         else std::printf("note: oracle/_ref/libastre_ref.so not found -- comparison with the reference build skipped\n");
+        const long long damaged = astre_gpu_debug_guard_check();     // ASTRE_GUARD=1: canaries around every device buffer
+        EXPECT(damaged <= 0);
+        if (damaged >= 0) std::printf("device buffer guards: %lld damaged bytes\n", damaged);
     }
     std::printf("%s: %d checks, %d failures%s\n", g_failures ? "FAILED" : "PASSED", g_checks, g_failures, cpu_only ? " (cpu-only subset)" : "");
     return g_failures ? 1 : 0;

@@ -286,6 +286,18 @@ def test_visible_world_gather(oracle):
     assert np.array_equal(oracle_lib.bits(vis), oracle_lib.bits(world[slots]))
 
 
+def test_buffer_guards_are_armed(gpu_lib):
+    """The canaries around the library's device buffers (ASTRE_GUARD=1, set in conftest.py) see a deliberate overrun,
+    and no test so far has damaged one."""
+    assert gpu_lib.astre_gpu_debug_guard_selftest() == 4
+    with GpuContext(5000, max_views=2) as ctx:
+        s = scenes.config1(5000)
+        scenes.load_into(ctx, s)
+        ctx.frame()
+        ctx.read_all_keys()
+        assert gpu_lib.astre_gpu_debug_guard_check() == 0
+
+
 def test_capacity_overflow_is_reported():
     s = scenes.config1(50_000)
     s.pos = (s.pos * np.float32(0.01)).astype(np.float32)
