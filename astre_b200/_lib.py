@@ -51,6 +51,10 @@ SIGNATURES = {
     "astre_gpu_debug_sort_keys": (C.c_int, [_P, _U64, C.c_uint64, C.c_uint64, C.c_uint32, _U64, _U32]),
     "astre_gpu_set_counts_mirror": (C.c_int, [_P, _P, _P]),
     "astre_gpu_frame_index": (C.c_int, [_P, _U64]),
+    "astre_gpu_count_board_create": (C.c_int, [_P, C.c_uint32, _P, C.POINTER(_P)]),
+    "astre_gpu_count_board_attach": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "astre_gpu_count_board_exchange": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "astre_gpu_count_board_status": (C.c_int, [_P, _U32, _U32]),
     "astre_gpu_global_offsets_dev": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "astre_gpu_debug_guard_check": (C.c_int64, []),
     "astre_gpu_debug_guard_selftest": (C.c_int64, []),

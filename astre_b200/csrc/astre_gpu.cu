@@ -151,6 +151,10 @@ struct astre_gpu_ctx {
     uint32_t cap_bin_bits = 0;            // log2 of the bins allocated
     uint32_t *d_chunk_first = nullptr;    // key sort: first bucket of every 1024-key chunk
     CountsMirror counts_mirror{{nullptr, nullptr}};   // astre_gpu_set_counts_mirror
+    BoardPeers board_peers{};             // astre_gpu_count_board_attach
+    CountBoard *d_board = nullptr;        // this rank's count board (astre_gpu_count_board_create); peers map it through CUDA IPC
+    uint32_t board_cap = 0;               // counts per rank and slot it holds
+    uint32_t *d_board_table = nullptr;    // [kBoardRanks][board_cap]: where astre_gpu_count_board_offsets puts the table by default
     FrameResultHost *h_res = nullptr;     // mapped host block the frame's last launch writes: key total (also the hint that sizes
     FrameResultHost *d_res = nullptr;     // the next frame's buckets), sort outcome, counts and offsets -- read after one sync, no copy
     uint32_t force_lsd = 0;               // ASTRE_SORT_FORCE_LSD=1: always take the LSD fallback (tests)
@@ -607,7 +611,9 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
     {
         int occ_sort = 0;
         CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sort, k_sort_lsd_all, kSortThreads, 0));
-        ctx->sort_grid = ctx->sm_count * std::max(occ_sort, 1);     // co-resident: the fallback has grid barriers
+        // the fallback has grid barriers, so its CTAs must all be resident at once -- also while a small kernel of
+        // another stream (a count-board receive, a collective) holds a few CTA slots until a peer GPU answers
+        ctx->sort_grid = std::max(ctx->sm_count * std::max(occ_sort, 1) - 8, 1);
     }
     CKC(cudaEventCreate(&ctx->ev_begin));
     CKC(cudaEventCreate(&ctx->ev_cull0));
@@ -664,6 +670,8 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
     for (void *p : ptrs) if (p) dev_free(p);
     for (unsigned char *p : ctx->d_publish) if (p) cudaFree(p);
+    if (ctx->d_board) cudaFree(ctx->d_board);
+    if (ctx->d_board_table) dev_free(ctx->d_board_table);
     for (void *p : ctx->imports) cudaIpcCloseMemHandle(p);
     cudaEvent_t evs[] = { ctx->ev_begin, ctx->ev_cull0, ctx->ev_cull1, ctx->ev_end, ctx->ev_merge0, ctx->ev_merge1, ctx->ev_views };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
@@ -1422,6 +1430,75 @@ int astre_gpu_set_counts_mirror(astre_gpu_ctx *ctx, void *dev_slot0, void *dev_s
     ctx->counts_mirror.slot[0] = static_cast<uint32_t *>(dev_slot0);
     ctx->counts_mirror.slot[1] = static_cast<uint32_t *>(dev_slot1);
     ++ctx->params_version;             // kernel parameters of a captured frame graph
+    return ASTRE_OK;
+}
+
+// ---- count boards: the 8e exchange as one kernel over peer memory (kernels_mirror.cuh) -----------------------------
+
+int astre_gpu_count_board_create(astre_gpu_ctx *ctx, uint32_t max_counts, void *ipc_handle_out, void **board_dev_out)
+{
+    if (!ctx || max_counts == 0) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "max_counts must be positive") : ASTRE_ERR_INVALID;
+    if (ctx->d_board) return fail(ctx, ASTRE_ERR_STATE, "this context already has a count board");
+    CK(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CK(cudaMalloc(&p, board_bytes(max_counts)));      // not guarded: peers map this allocation by its base address (CUDA IPC)
+    CK(cudaMemset(p, 0, board_bytes(max_counts)));
+    CK(cudaDeviceSynchronize());
+    ctx->d_board = static_cast<CountBoard *>(p);
+    ctx->board_cap = max_counts;
+    CK(dev_alloc(&ctx->d_board_table, (size_t)kBoardRanks * max_counts * sizeof(uint32_t)));
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, p));
+        std::memcpy(ipc_handle_out, &h, sizeof h);
+    }
+    if (board_dev_out) *board_dev_out = p;
+    return ASTRE_OK;
+}
+
+int astre_gpu_count_board_attach(astre_gpu_ctx *ctx, uint32_t world_size, uint32_t rank, void *const *boards)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (!ctx->d_board) return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_count_board_create has not been called");
+    if (world_size == 0 || world_size > kBoardRanks || rank >= world_size)
+        return fail(ctx, ASTRE_ERR_INVALID, "count boards connect 1..%u ranks, got rank %u of %u", kBoardRanks, rank, world_size);
+    if (world_size > 1 && !boards) return fail(ctx, ASTRE_ERR_INVALID, "boards is null");
+    BoardPeers B{};
+    for (uint32_t t = 0; t < world_size; ++t) {
+        B.b[t] = t == rank ? ctx->d_board : static_cast<CountBoard *>(boards[t]);
+        if (!B.b[t]) return fail(ctx, ASTRE_ERR_INVALID, "board of rank %u is null", t);
+    }
+    B.own = ctx->d_board; B.n = world_size; B.self = rank; B.cap = ctx->board_cap;
+    ctx->board_peers = B;
+    return ASTRE_OK;
+}
+
+int astre_gpu_count_board_exchange(astre_gpu_ctx *ctx, const uint32_t *counts_dev, uint32_t n_counts, uint32_t rank_major,
+                                   uint32_t *table_dev, uint64_t *offsets_dev, uint64_t *view_totals_dev, void *stream)
+{
+    if (!ctx || (n_counts && !counts_dev)) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "counts_dev is null") : ASTRE_ERR_INVALID;
+    const BoardPeers &B = ctx->board_peers;
+    if (!B.n) return fail(ctx, ASTRE_ERR_STATE, "no count board attached");
+    if (n_counts > B.cap) return fail(ctx, ASTRE_ERR_INVALID, "%u counts exceed the board's capacity %u", n_counts, B.cap);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    k_board_exchange<<<1, 256, 0, s>>>(B, counts_dev, n_counts, rank_major, table_dev ? table_dev : ctx->d_board_table,
+                                       reinterpret_cast<unsigned long long *>(offsets_dev),
+                                       reinterpret_cast<unsigned long long *>(view_totals_dev));
+    CK_LAUNCH();
+    return ASTRE_OK;
+}
+
+int astre_gpu_count_board_status(astre_gpu_ctx *ctx, uint32_t *exchanges, uint32_t *error)
+{
+    if (!ctx) return ASTRE_ERR_INVALID;
+    if (!ctx->d_board) return fail(ctx, ASTRE_ERR_STATE, "astre_gpu_count_board_create has not been called");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CountBoard h;
+    CK(cudaMemcpy(&h, ctx->d_board, sizeof h, cudaMemcpyDeviceToHost));
+    if (exchanges) *exchanges = h.round;
+    if (error) *error = h.error;
     return ASTRE_OK;
 }
 

@@ -223,9 +223,10 @@ k_run_write(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t cl
 // all-gathered table [world_size][n_views]; the global list is ordered (view, rank, key), so
 // offsets[v] = sum of every view before v over all ranks + sum of view v over the ranks before this one.
 // One block (the table is tiny: n_views <= worlds x views of one shard).
-__global__ void __launch_bounds__(256)
-k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, uint32_t rank, uint32_t n_views,
-                 uint32_t rank_major, unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
+// (`stride` = distance in words between the rows of two ranks; the plain table has stride n_views.)
+__device__ __forceinline__ void global_offsets_block(const uint32_t *all_counts, const size_t stride, uint32_t world_size, uint32_t rank,
+                                                     uint32_t n_views, uint32_t rank_major, unsigned long long *__restrict__ offsets,
+                                                     unsigned long long *__restrict__ view_totals)
 {
     __shared__ unsigned long long s_warp[8];
     __shared__ unsigned long long s_carry;
@@ -235,7 +236,7 @@ k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, u
     if (rank_major) {
         // whole-world shards: everything of the earlier ranks comes first, then this rank's units in order
         unsigned long long mine = 0;
-        for (size_t i = threadIdx.x; i < (size_t)rank * n_views; i += 256u) mine += all_counts[i];
+        for (size_t i = threadIdx.x; i < (size_t)rank * n_views; i += 256u) mine += all_counts[(i / n_views) * stride + i % n_views];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
         if (lane == 0) s_warp[warp] = mine;
@@ -248,10 +249,10 @@ k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, u
         unsigned long long total = 0, before = 0;
         if (v < n_views) {
             if (rank_major) {
-                total = all_counts[(size_t)rank * n_views + v];
+                total = all_counts[(size_t)rank * stride + v];
             } else {
                 for (uint32_t r = 0; r < world_size; ++r) {
-                    const unsigned long long c = all_counts[(size_t)r * n_views + v];
+                    const unsigned long long c = all_counts[(size_t)r * stride + v];
                     if (r < rank) before += c;
                     total += c;
                 }
@@ -271,6 +272,113 @@ k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, u
         __syncthreads();
         if (threadIdx.x == 255) s_carry = off + incl;
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_global_offsets(const uint32_t *__restrict__ all_counts, uint32_t world_size, uint32_t rank, uint32_t n_views,
+                 uint32_t rank_major, unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
+{
+    global_offsets_block(all_counts, n_views, world_size, rank, n_views, rank_major, offsets, view_totals);
+}
+
+// ---- count boards: the 8e exchange (all-gather of the counts + segment offsets) as ONE kernel over peer memory ----
+//
+// Every rank owns one CountBoard in its own HBM, mapped by its peers through CUDA IPC.  k_board_exchange, one block on
+// a side stream, (1) STORES this rank's counts of a frame into the board of every rank over NVLink -- nobody ever
+// reads remote memory --, (2) waits until the counts of all ranks have landed in its own board, (3) writes the table
+// [n_ranks][n_counts], this rank's segment offsets and the per-view totals (k_global_offsets' arithmetic) and
+// (4) acknowledges the frame to every rank.  Every count travels as one 8-byte word {count, exchange number}: an 8-byte
+// store arrives whole, so a word whose upper half shows the expected number IS that exchange's count -- no flag, no
+// fence and no ordering between the stores is needed (the low-latency protocol of collective libraries).  Exchanges
+// are numbered per board on the device (`round`), exchange e uses slot e % kBoardSlots, which a rank rewrites only
+// after every peer has acknowledged exchange e - kBoardSlots: ranks may be up to kBoardSlots exchanges apart.
+constexpr uint32_t kBoardSlots = 4;
+constexpr uint32_t kBoardRanks = 8;             // GPUs of one NVSwitch node
+constexpr long long kBoardTimeoutCycles = 4000000000ll;      // ~2 s: a peer that never answers must not hang the GPU
+
+struct CountBoard {
+    uint32_t ack[kBoardRanks];                  // ack[t] = e: rank t has finished exchange e (stored by rank t)
+    uint32_t round;                             // exchanges the owner has finished
+    uint32_t error;                             // 1 + the rank that did not answer in time (sticky)
+    uint32_t pad[64 - kBoardRanks - 2];
+    // words[kBoardSlots][kBoardRanks][cap] follow: {count, exchange number} of rank t's count i in slot s
+};
+static_assert(sizeof(CountBoard) == 256, "CountBoard layout");
+
+__host__ __device__ __forceinline__ unsigned long long *board_words(CountBoard *b, uint32_t slot, uint32_t rank, uint32_t cap)
+{
+    return reinterpret_cast<unsigned long long *>(b + 1) + ((size_t)slot * kBoardRanks + rank) * cap;
+}
+__host__ __device__ constexpr size_t board_bytes(uint32_t cap) { return sizeof(CountBoard) + (size_t)kBoardSlots * kBoardRanks * cap * 8; }
+
+struct BoardPeers {
+    CountBoard *b[kBoardRanks];                 // b[self] is the owner's board (a local pointer), the others are IPC mappings
+    CountBoard *own;
+    uint32_t n, self, cap;                      // n == 0: no board attached
+};
+
+// relaxed, system scope: never served from (or parked in) a non-coherent cache
+__device__ __forceinline__ uint32_t ld_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__global__ void __launch_bounds__(256)
+k_board_exchange(const BoardPeers B, const uint32_t *__restrict__ counts, const uint32_t n_counts, const uint32_t rank_major,
+                 uint32_t *__restrict__ table, unsigned long long *__restrict__ offsets, unsigned long long *__restrict__ view_totals)
+{
+    const uint32_t e = ld_sys_u32(&B.own->round) + 1u, slot = e % kBoardSlots, n = min(n_counts, B.cap);
+    const long long t0 = clock64();
+    // (1) the slot still holds exchange e - kBoardSlots on every rank that has not finished it (in steady state all have)
+    if (e > kBoardSlots) {
+        if (threadIdx.x < B.n)
+            while (ld_sys_u32(&B.own->ack[threadIdx.x]) < e - kBoardSlots) {
+                if (clock64() - t0 > kBoardTimeoutCycles) { B.own->error = 1u + threadIdx.x; break; }
+                __nanosleep(100);
+            }
+        __syncthreads();
+    }
+#pragma unroll
+    for (uint32_t t = 0; t < kBoardRanks; ++t)          // (static indices: the parameter stays in the constant bank)
+        if (t < B.n) {
+            unsigned long long *dst = board_words(B.b[t], slot, B.self, B.cap);
+            for (uint32_t i = threadIdx.x; i < n; i += 256u) st_sys_u64(dst + i, (unsigned long long)e << 32 | counts[i]);
+        }
+    // (2) everybody's counts of exchange e, out of this rank's own memory
+    for (uint32_t t = 0; t < B.n; ++t) {
+        const unsigned long long *src = board_words(B.own, slot, t, B.cap);
+        for (uint32_t i = threadIdx.x; i < n; i += 256u) {
+            unsigned long long w;
+            while ((uint32_t)((w = ld_sys_u64(src + i)) >> 32) != e) {
+                if (clock64() - t0 > kBoardTimeoutCycles) { B.own->error = 1u + t; break; }
+                __nanosleep(100);
+            }
+            table[(size_t)t * n + i] = (uint32_t)w;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // (3)
+    global_offsets_block(table, n, B.n, B.self, n, rank_major, offsets, view_totals);
+    __syncthreads();
+    // (4)
+    if (threadIdx.x == 0) {
+        B.own->round = e;
+        __threadfence_system();                 // the loads above are done before a peer may rewrite the slot
+#pragma unroll
+        for (uint32_t t = 0; t < kBoardRanks; ++t)
+            if (t < B.n) st_sys_u32(&B.b[t]->ack[B.self], e);
     }
 }
 

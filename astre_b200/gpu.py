@@ -139,6 +139,30 @@ class GpuContext:
         """Frame k also writes its per-view counts to device buffer ptr[k & 1] (k = frame_index()); 0, 0 switches it off."""
         self._check(self._lib.astre_gpu_set_counts_mirror(self._h, int(ptr0) or None, int(ptr1) or None))
 
+    # ---- count boards (8e as stores into peer memory) ----
+    def count_board_create(self, max_counts):
+        """Allocates this context's count board -> (CUDA IPC handle as bytes, local device pointer)."""
+        buf = (C.c_ubyte * 64)()
+        out = C.c_void_p()
+        self._check(self._lib.astre_gpu_count_board_create(self._h, int(max_counts), buf, C.byref(out)))
+        return bytes(buf), out.value
+
+    def count_board_attach(self, world_size, rank, board_ptrs):
+        """board_ptrs[t]: device pointer of rank t's board (own entry ignored)."""
+        ptrs = (C.c_void_p * int(world_size))(*[int(p) if p else None for p in board_ptrs])
+        self._check(self._lib.astre_gpu_count_board_attach(self._h, int(world_size), int(rank), ptrs))
+
+    def count_board_exchange(self, counts_ptr, n_counts, offsets_ptr, totals_ptr=0, table_ptr=0, stream=None, rank_major=False):
+        """Enqueues one exchange: counts (device) -> every rank's board -> table [world, n_counts], offsets, totals (device)."""
+        self._check(self._lib.astre_gpu_count_board_exchange(self._h, int(counts_ptr) or None, int(n_counts), 1 if rank_major else 0,
+                                                             int(table_ptr) or None, int(offsets_ptr) or None, int(totals_ptr) or None, stream))
+
+    def count_board_status(self):
+        """(exchanges finished, error) of this rank's board; synchronises the device."""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.astre_gpu_count_board_status(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def frame_index(self):
         v = C.c_uint64()
         self._check(self._lib.astre_gpu_frame_index(self._h, C.byref(v)))

@@ -114,6 +114,7 @@ class CountExchange:
         torch.cuda.synchronize(self.device)
         self.ctx.set_counts_mirror(0, 0)
 
+
     def before_frame(self):
         """Call before ctx.frame(): the slot the coming frame writes must not be in use by an exchange any more."""
         p = (self.ctx.frame_index() + 1) & 1
@@ -128,17 +129,21 @@ class CountExchange:
         self.framed[p].record(main)
         self.side.wait_event(self.framed[p])
         with torch.cuda.stream(self.side):
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.table[p].view(-1), self.slot[p], group=self.group)
-            else:
-                self.table[p].view(-1).copy_(self.slot[p], non_blocking=True)
-            self.ctx.global_offsets_dev(self.table[p].data_ptr(), self.world, self.rank, self.n,
-                                        self.offsets[p].data_ptr(), self.totals[p].data_ptr(), self.side.cuda_stream,
-                                        rank_major=self.rank_major)
+            self._exchange(p)
             self.done[p].record(self.side)
         self.busy[p] = True
         self.last_slot = p
         return p
+
+    def _exchange(self, p):
+        """On the side stream: slot p -> table p, offsets p, totals p."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.table[p].view(-1), self.slot[p], group=self.group)
+        else:
+            self.table[p].view(-1).copy_(self.slot[p], non_blocking=True)
+        self.ctx.global_offsets_dev(self.table[p].data_ptr(), self.world, self.rank, self.n,
+                                    self.offsets[p].data_ptr(), self.totals[p].data_ptr(), self.side.cuda_stream,
+                                    rank_major=self.rank_major)
 
     def finish(self):
         torch.cuda.current_stream(self.device).wait_stream(self.side)
@@ -149,6 +154,47 @@ class CountExchange:
         self.done[p].synchronize()
         return (self.table[p].cpu().numpy().astype(np.uint32), self.offsets[p].cpu().numpy().astype(np.uint64),
                 self.totals[p].cpu().numpy().astype(np.uint64))
+
+
+class PeerCountExchange(CountExchange):
+    """The same exchange with no collective library on the path: count boards (astre_gpu_count_board_*).  Every rank's
+    board lives in its own HBM and is mapped by the peers through CUDA IPC; per frame ONE one-block kernel on the side
+    stream stores this rank's counts into all boards over NVLink, waits for everybody's, and writes the table, this
+    rank's segment offsets and the per-view totals -- all-gather and offsets fused over peer memory.  The frame itself
+    only mirrors its counts into a slot, exactly as for CountExchange.  `boards` / `rank` / `world`: device pointers of
+    all ranks' boards when the ranks live in one process (tests); otherwise the IPC handles are exchanged once."""
+
+    def __init__(self, ctx, n_counts, group=None, device=None, rank_major=False, boards=None, rank=None, world=None):
+        super().__init__(ctx, n_counts, group=group, device=device, rank_major=rank_major)
+        if rank is not None:
+            self.rank, self.world = int(rank), int(world)
+            self.table = [torch.zeros((self.world, self.n), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self.imports = []
+        if boards is None:          # one process per GPU: exchange the IPC handles once
+            handle, own = ctx.count_board_create(self.n)
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, (self.n, handle), group=group)
+                if any(h[0] != self.n for h in handles):
+                    raise ValueError(f"count boards need the same number of counts on every rank, got {[h[0] for h in handles]}")
+            boards = [own if r == self.rank else ctx.import_handle(handles[r][1]) for r in range(self.world)]
+            self.imports = [b for r, b in enumerate(boards) if r != self.rank]
+        ctx.count_board_attach(self.world, self.rank, boards)
+
+    def close(self):
+        super().close()
+        exchanges, error = self.ctx.count_board_status()
+        if error:
+            raise RuntimeError(f"count board: rank {error - 1} did not answer in time (exchange {exchanges + 1})")
+        if self.imports and dist.is_initialized():
+            dist.barrier(group=self.group)         # nobody unmaps a board a peer may still be storing into
+        for p in self.imports:
+            self.ctx.release_import(p)
+        self.imports = []
+
+    def _exchange(self, p):
+        self.ctx.count_board_exchange(self.slot[p].data_ptr(), self.n, self.offsets[p].data_ptr(), self.totals[p].data_ptr(),
+                                      self.table[p].data_ptr(), stream=self.side.cuda_stream, rank_major=self.rank_major)
 
 
 class GlobalDrawList:

@@ -8,9 +8,11 @@ hot path (fused transform + frustum cull + compaction + 64-bit draw-key sort) ov
 
   headline   N = 1: configuration 3 (16,777,216 flat entities, camera + 4 shadow-cascade frusta).
              N > 1: every rank owns its own 16,777,216-entity range of the configuration-4 stream (weak scaling)
-             and the per-frame exchange of SURVEY.md 8e runs every step: NCCL all-gather of the per-shard visible
-             counts + this rank's segment offsets (astre_gpu_global_offsets_dev), on a side stream, off the
-             frame's critical path; the timed region ends only when the last exchange has finished.
+             and the per-frame exchange of SURVEY.md 8e runs every step, on a side stream, off the frame's critical
+             path: one kernel stores the per-shard visible counts into every rank's count board over NVLink, waits
+             for everybody's and derives this rank's segment offsets (astre_gpu_count_board_exchange; no collective
+             library on the path); --exchange nccl uses an NCCL all-gather + astre_gpu_global_offsets_dev instead.
+             The timed region ends only when the last exchange has finished.
   extras     (top-level key `extra_workloads`, unless --no-extra) the other BASELINE.json configurations, each with its own
              value / roofline / e2e / cpu_baseline / parity: config 1 (10k flat, N = 1 only), config 2 (1M, 8-level
              hierarchy; root-subtree shards), config 4 (67,108,864 flat FIXED, entity-range shards: strong
@@ -154,7 +156,7 @@ def make_workload(name, rank, world):
 def headline_config(workload, n, views, visible_keys, world):
     """The `config` object of the JSON line -- built by BOTH arms from the same values, so that they compare equal."""
     return {"workload": workload + "; transform + frustum cull + compaction + 64-bit draw-key sort"
-                        + ("; per-frame exchange of per-shard visible counts (NCCL all-gather) and segment offsets" if world > 1 else ""),
+                        + ("; per-frame exchange of per-shard visible counts and segment offsets" if world > 1 else ""),
             "entities_per_gpu": int(n), "views": int(views), "visible_keys_rank0": int(visible_keys),
             "l2": f"inputs ({n * 44 / 1e6:.0f} MB/GPU) and outputs ({n * 64 / 1e6:.0f} MB/GPU) exceed the 126 MB L2; no flush"
                   if n * 108 > 4 * 126e6 else "working set fits the 126 MB L2: launch-latency regime, stated as such"}
@@ -285,7 +287,7 @@ def run_reference(args):
 class Bench:
     """One workload on this rank's GPU: device-resident timing, dominant-kernel timing, end to end, parity."""
 
-    def __init__(self, name, rank, local_rank, world, torch, dist, use_graph=True):
+    def __init__(self, name, rank, local_rank, world, torch, dist, use_graph=True, exchange="p2p"):
         from astre_b200 import GpuContext, gpu, multi, scenes
         self.torch, self.dist, self.gpu, self.multi = torch, dist, gpu, multi
         self.name, self.rank, self.world = name, rank, world
@@ -301,7 +303,11 @@ class Bench:
         assert self.stream.cuda_stream != 0
         self.ctx.set_stream(self.stream.cuda_stream)
         self.rank_major = s.n_worlds > 1          # whole-world shards: the global list is the concatenation of the ranks' lists
-        self.exchange = multi.CountExchange(self.ctx, self.n_counts, rank_major=self.rank_major) if world > 1 and name != "config1" else None
+        self.exchange_kind = exchange
+        self.exchange = None
+        if (world > 1 or os.environ.get("ASTRE_BENCH_FORCE_EXCHANGE")) and name != "config1":     # (the variable: exchange path on one GPU)
+            cls = multi.PeerCountExchange if exchange == "p2p" else multi.CountExchange
+            self.exchange = cls(self.ctx, self.n_counts, rank_major=self.rank_major)
         # steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
         self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph else 0)
         self.e2e_flags = self.frame_flags | gpu.FRAME_GATHER     # end-to-end steps read the list's matrices back: gathered in-frame
@@ -321,8 +327,8 @@ class Bench:
         if self.exchange is None:
             self.ctx.frame(self.frame_flags)
             return
-        # the frame's last kernel mirrors the counts into a slot; the exchange (all-gather + offsets) runs on a side
-        # stream while the next frames compute
+        # the frame's last kernel mirrors the counts into a slot; the exchange (count boards: one kernel over peer memory;
+        # nccl: all-gather + offsets kernel) runs on a side stream while the next frames compute
         self.exchange.before_frame()
         self.ctx.frame(self.frame_flags)
         self.exchange.after_frame()
@@ -374,8 +380,10 @@ class Bench:
             self.scaling_detail = {"ms_per_step_min_over_ranks": -self.max_over_ranks(-own_ms), "ms_per_step_max_over_ranks": ms_step,
                                    "without_exchange_ms_min_over_ranks": -self.max_over_ranks(-plain),
                                    "without_exchange_ms_max_over_ranks": self.max_over_ranks(plain),
-                                   "note": "ranks advance in step (a count slot is reused only when its exchange is done), so every rank "
-                                           "runs at the pace of the slowest GPU; exchange cost = max - without_exchange max"}
+                                   "exchange": self.exchange_kind,
+                                   "note": "ranks are coupled through the exchange (a count slot is reused only when every rank has consumed "
+                                           "it), so all ranks run at the pace of the slowest GPU; "
+                                           "exchange cost = max - without_exchange max"}
         # torch-issued kernels inside the step at N > 1: staging copy + NCCL all-gather per frame (not counted as ours)
         return ms_step, launches
 
@@ -505,7 +513,7 @@ class Bench:
 
 
 def run_workload(name, rank, local_rank, world, args, torch, dist, steps, warmup, e2e_steps, cpu_reps, headline):
-    b = Bench(name, rank, local_rank, world, torch, dist, use_graph=not args.no_graph)
+    b = Bench(name, rank, local_rank, world, torch, dist, use_graph=not args.no_graph, exchange=args.exchange)
     try:
         ms_step, launches = b.device_resident(steps, warmup)
         kernel_ms = b.kernel_timing(min(steps, 20))
@@ -535,6 +543,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip config.extra_workloads")
     ap.add_argument("--entities", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: count boards (stores into peer memory, default) or an NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true", help="launch the frame kernel by kernel instead of replaying one CUDA graph")
     args = ap.parse_args()
     if args.entities:

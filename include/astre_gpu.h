@@ -374,6 +374,28 @@ ASTRE_API void astre_global_offsets_rank_major(const uint32_t *all_counts, uint3
 /* The same on the device and stream-ordered, for an all-gathered count table that never leaves the GPU
  * (all pointers are device pointers; offsets_dev / view_totals_dev may be NULL): the per-frame exchange of
  * SURVEY.md 8e then needs no host round trip.  rank_major != 0: the layout of astre_global_offsets_rank_major.  stream: cudaStream_t cast to void* (NULL = the context's). */
+/* ---- count boards: the exchange of SURVEY.md 8e as ONE kernel over peer memory, no collective library ----
+ * Every rank owns a board in its own HBM that its peers map (CUDA IPC, or the plain device pointer inside one
+ * process).  astre_gpu_count_board_exchange enqueues a one-block kernel that stores this rank's counts (counts_dev:
+ * device memory, e.g. a slot of astre_gpu_set_counts_mirror) into the board of every rank over NVLink -- each count
+ * as one 8-byte word tagged with the exchange number, so no flag, fence or ordering is needed --, waits (bounded,
+ * ~2 s) until the counts of all ranks have landed in its own board, writes the table [world_size][n_counts]
+ * (table_dev, nullable), this rank's segment offsets and the per-view totals (as astre_gpu_global_offsets_dev) and
+ * acknowledges.  All ranks call it the same number of times with the same n_counts; a rank may be up to 4 exchanges
+ * ahead of the slowest.  The kernel waits for peers: enqueue it on a stream other than the one the frames run on.
+ * Spec-defined (the reference is single-process).
+ *
+ * create: allocates the board for up to max_counts counts per rank; ipc_handle_out (ASTRE_IPC_HANDLE_BYTES,
+ *   nullable) receives the handle peers open with astre_gpu_import_handle, *board_dev_out (nullable) the local pointer.
+ * attach: boards[t] = device pointer of rank t's board (boards[rank] is ignored).  Every rank must have created
+ *   its board before any rank exchanges.
+ * status: exchanges this rank has finished and the sticky error (0, or 1 + the rank that did not answer in time);
+ *   synchronises the device. */
+ASTRE_API int astre_gpu_count_board_create(astre_gpu_ctx *ctx, uint32_t max_counts, void *ipc_handle_out, void **board_dev_out);
+ASTRE_API int astre_gpu_count_board_attach(astre_gpu_ctx *ctx, uint32_t world_size, uint32_t rank, void *const *boards);
+ASTRE_API int astre_gpu_count_board_exchange(astre_gpu_ctx *ctx, const uint32_t *counts_dev, uint32_t n_counts, uint32_t rank_major,
+                                             uint32_t *table_dev, uint64_t *offsets_dev, uint64_t *view_totals_dev, void *stream);
+ASTRE_API int astre_gpu_count_board_status(astre_gpu_ctx *ctx, uint32_t *exchanges, uint32_t *error);
 /* Frame k (astre_gpu_frame_index, counted from 1 and wrapping at 2^27) also leaves its per-(world, view) counts in
  * dev_slot[k & 1] (device memory of the caller, uint32[n_worlds * views] each): the exchange of SURVEY.md 8e can
  * then read them on another stream while frame k+1 -- which zeroes the live counters -- is already running.

@@ -619,6 +619,100 @@ def test_count_exchange_single_rank(oracle):
             ctx.set_stream(None)
 
 
+def test_count_boards_single_rank(oracle):
+    """multi.PeerCountExchange without peers: the side-stream kernel pushes the mirrored counts into the rank's own board
+    and turns them into table + offsets; more exchanges than board slots, plain and graph frames mixed."""
+    import torch
+    from astre_b200 import multi
+    for scene, rank_major in ((scenes.config3(200_000), False), (scenes.config5(n_worlds=32, entities_per_world=1024), True)):
+        n_counts = scene.n_worlds * scene.views_per_world
+        with GpuContext(scene.n, max_views=scene.views_per_world) as ctx:
+            scenes.load_into(ctx, scene)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                ctx.set_stream(stream.cuda_stream)
+                ex = multi.PeerCountExchange(ctx, n_counts, rank_major=rank_major)
+                for k in range(11):
+                    if k == 6:                                   # the scene changes between frames
+                        scene.pos = (scene.pos * np.float32(0.5)).astype(np.float32)
+                        ctx.update_trs_range(0, scene.n, scene.pos, scene.rot, scene.scale)
+                    ex.before_frame()
+                    ctx.frame(gpu.FRAME_ALL | (gpu.FRAME_GRAPH if k % 3 else 0))
+                    ex.after_frame()
+                    if k in (2, 5, 10):
+                        table, off, tot = ex.last()
+                        _, _, o_counts = oracle.frame(scene)
+                        assert np.array_equal(table[0], o_counts)
+                        h_off, h_tot = gpu.global_offsets(table, 0, rank_major)
+                        assert np.array_equal(off, h_off) and np.array_equal(tot, h_tot)
+                        assert np.array_equal(ctx.read_counts(), o_counts)
+                ex.close()
+                assert ctx.count_board_status() == (11, 0)
+            ctx.set_stream(None)
+
+
+def test_count_boards_two_ranks_on_one_gpu(oracle):
+    """Two contexts of one process act as two ranks (their boards are plain device pointers to each other): the whole
+    protocol -- stores into the peer's board, tagged words, acknowledgements, slot reuse after 4 exchanges, one rank
+    running ahead of the other -- with every checked frame's table and offsets compared against the host formula."""
+    import torch
+    from astre_b200 import multi
+    halves = [scenes.config4(240_000, 0, 120_000), scenes.config4(240_000, 120_000, 240_000)]
+    n_counts = halves[0].views_per_world
+    want = [oracle.frame(h)[2] for h in halves]
+    ctxs = [GpuContext(h.n, max_views=n_counts) for h in halves]
+    streams = [torch.cuda.Stream() for _ in ctxs]
+    try:
+        boards = []
+        for c, h, st in zip(ctxs, halves, streams):
+            scenes.load_into(c, h)
+            c.set_stream(st.cuda_stream)
+            boards.append(c.count_board_create(n_counts)[1])
+        ex = []
+        for r, (c, st) in enumerate(zip(ctxs, streams)):
+            with torch.cuda.stream(st):
+                ex.append(multi.PeerCountExchange(c, n_counts, boards=boards, rank=r, world=2))
+
+        def frames(r, k, graph):
+            with torch.cuda.stream(streams[r]):
+                for _ in range(k):
+                    ex[r].before_frame()
+                    ctxs[r].frame(gpu.FRAME_ALL | (gpu.FRAME_GRAPH if graph else 0))
+                    ex[r].after_frame()
+
+        def check(r):
+            table, off, tot = ex[r].last()
+            assert np.array_equal(table[0], want[0]) and np.array_equal(table[1], want[1]), (r, table)
+            h_off, h_tot = gpu.global_offsets(table, r, False)
+            assert np.array_equal(off, h_off) and np.array_equal(tot, h_tot)
+
+        frames(0, 3, False); frames(1, 3, False)           # rank 0 enqueues three frames before rank 1 has any
+        check(0); check(1)
+        frames(1, 2, True); frames(0, 4, True); frames(1, 3, True); frames(0, 1, True)      # 8 each: every slot reused
+        check(0); check(1)
+        # one rank's scene changes: the other must see the new counts in the very next table
+        halves[1].pos = (halves[1].pos * np.float32(0.25)).astype(np.float32)
+        ctxs[1].update_trs_range(0, halves[1].n, halves[1].pos, halves[1].rot, halves[1].scale)
+        want[1] = oracle.frame(halves[1])[2]
+        frames(0, 1, True); frames(1, 1, True)
+        check(0); check(1)
+        frames(1, 2, False); frames(0, 2, True)
+        check(0); check(1)
+        for r in (0, 1):
+            with torch.cuda.stream(streams[r]):
+                ex[r].finish()
+        torch.cuda.synchronize()
+        for c in ctxs:
+            assert c.count_board_status() == (11, 0)
+        for r in (0, 1):
+            with torch.cuda.stream(streams[r]):
+                ex[r].close()
+    finally:
+        for c in ctxs:
+            c.set_stream(None)
+            c.close()
+
+
 def test_gather_inside_the_frame(oracle):
     """ASTRE_FRAME_GATHER: the list's world matrices are produced by the frame itself; short lists (<= 4096 keys) arrive
     in host memory with no copy, longer ones need two copies and no launch, lists beyond the gather buffer fall back."""

@@ -209,6 +209,23 @@ def test_multi_gpu_merge():
     assert r.returncode == 0 and "MERGE_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.gpu
+def test_multi_gpu_count_boards():
+    """One process per GPU (all of the box's GPUs, at least two): the count exchange as stores into peer memory."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n_gpus = torch.cuda.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n_gpus, 8)), "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(here, "board_worker.py"), "400000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "BOARD_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def _merge_kat():
     import json
     import os
