@@ -624,7 +624,8 @@ def test_count_boards_single_rank(oracle):
     and turns them into table + offsets; more exchanges than board slots, plain and graph frames mixed."""
     import torch
     from astre_b200 import multi
-    for scene, rank_major in ((scenes.config3(200_000), False), (scenes.config5(n_worlds=32, entities_per_world=1024), True)):
+    for scene, rank_major in ((scenes.config3(200_000), False), (scenes.config5(n_worlds=32, entities_per_world=1024), True),
+                              (scenes.config5(n_worlds=600, entities_per_world=64), True)):      # 600 counts: more than one block pass
         n_counts = scene.n_worlds * scene.views_per_world
         with GpuContext(scene.n, max_views=scene.views_per_world) as ctx:
             scenes.load_into(ctx, scene)
