@@ -306,8 +306,21 @@ class Bench:
         self.exchange_kind = exchange
         self.exchange = None
         if (world > 1 or os.environ.get("ASTRE_BENCH_FORCE_EXCHANGE")) and name != "config1":     # (the variable: exchange path on one GPU)
-            cls = multi.PeerCountExchange if exchange == "p2p" else multi.CountExchange
-            self.exchange = cls(self.ctx, self.n_counts, rank_major=self.rank_major)
+            if exchange == "p2p":
+                # count boards need CUDA IPC between the ranks' processes; if any rank cannot map its peers (a container
+                # without shared PID / IPC namespaces), ALL ranks use the NCCL variant and the line says so
+                err = ""
+                try:
+                    self.exchange = multi.PeerCountExchange(self.ctx, self.n_counts, rank_major=self.rank_major)
+                except Exception as e:      # noqa: BLE001
+                    err = f"{type(e).__name__}: {e}"
+                if self.max_over_ranks(1.0 if err else 0.0) > 0:
+                    print(f"bench.py: rank {rank}: count boards unavailable ({err or 'on another rank'}); using the NCCL exchange",
+                          file=sys.stderr, flush=True)
+                    self.exchange = None
+                    self.exchange_kind = "nccl (count boards unavailable)"
+            if self.exchange is None:
+                self.exchange = multi.CountExchange(self.ctx, self.n_counts, rank_major=self.rank_major)
         # steps replay the frame as one CUDA graph (ASTRE_FRAME_GRAPH); --no-graph launches kernel by kernel
         self.frame_flags = gpu.FRAME_ALL | (gpu.FRAME_GRAPH if use_graph else 0)
         self.e2e_flags = self.frame_flags | gpu.FRAME_GATHER     # end-to-end steps read the list's matrices back: gathered in-frame
