@@ -251,6 +251,7 @@ struct astre_gpu_ctx {
     uint64_t launches = 0;
     int fused_blocks_per_sm = 2;
     int cone_blocks_per_sm = 2;
+    uint32_t cone_prefetch = 1;      // ASTRE_CONE_PREFETCH=0: the cone kernel does not prefetch its inputs into L2 (measurement)
     bool coop_launch = false;        // device supports cooperative launches (multi-level hierarchy launches)
     bool use_pdl = true;             // programmatic dependent launch for the sort chain (ASTRE_NO_PDL disables)
     uint32_t small_flat = 262144;    // flat frames below this many entities take the thread-per-entity kernel too (ASTRE_SMALL_FLAT; measured: 10k 19.4 -> 9.7 us, 100k 20.6 -> 13.1, 250k 24.4 -> 21.0)
@@ -648,6 +649,7 @@ astre_gpu_ctx *astre_gpu_create(int device, uint32_t max_entities, uint32_t max_
         CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cones, k_hier_cones<true>, kBlockThreads, 0));
         ctx->cone_blocks_per_sm = std::max(occ_cones, 1);
         if (const char *m = std::getenv("ASTRE_CONES_PER_SM")) ctx->cone_blocks_per_sm = std::max(std::atoi(m), 1);
+        if (const char *m = std::getenv("ASTRE_CONE_PREFETCH")) ctx->cone_prefetch = std::atoi(m) != 0;
         if (std::getenv("ASTRE_NO_PDL")) ctx->use_pdl = false;
     }
     std::memset(&ctx->h_viewset, 0, sizeof(ViewSet));
@@ -1008,8 +1010,8 @@ int enqueue_frame(astre_gpu_ctx *ctx, const FramePlan &fp, cudaStream_t s, bool 
             pdl.val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(ctx->n_cones); cfg.blockDim = dim3(kBlockThreads); cfg.stream = s; cfg.attrs = &pdl; cfg.numAttrs = 1;
-            if (cull) CK(cudaLaunchKernelEx(&cfg, k_hier_cones<true>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
-            else CK(cudaLaunchKernelEx(&cfg, k_hier_cones<false>, P, bp, (const uint2 *)ctx->d_cones, n_levels));
+            if (cull) CK(cudaLaunchKernelEx(&cfg, k_hier_cones<true>, P, bp, (const uint2 *)ctx->d_cones, n_levels, ctx->cone_prefetch));
+            else CK(cudaLaunchKernelEx(&cfg, k_hier_cones<false>, P, bp, (const uint2 *)ctx->d_cones, n_levels, ctx->cone_prefetch));
             CK_LAUNCH();
         } else if (!ctx->has_parents && n < ctx->small_flat) {
             // a frame this small is all latency: one entity per thread finishes in a third of the tiled kernel's first tile

@@ -425,7 +425,8 @@ k_transform_cull_indexed(const FrameParams P, const __grid_constant__ BinPlan bp
 #endif
 template <bool CULL>
 __global__ void __launch_bounds__(kBlockThreads, ASTRE_CONE_MIN_BLOCKS)
-k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint2 *__restrict__ ranges, const uint32_t n_levels)
+k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint2 *__restrict__ ranges, const uint32_t n_levels,
+             const uint32_t prefetch)
 {
     constexpr uint32_t kBufKeys = CULL ? 3072u : 1u;          // per-CTA key buffer: ONE global reservation per flush
     __shared__ float4 s_scratch[kBlockThreads * 4];
@@ -441,6 +442,19 @@ k_hier_cones(const FrameParams P, const __grid_constant__ BinPlan bp, const uint
     const bool buffered = CULL && F * kBlockThreads <= kBufKeys / 2u;
     if (threadIdx.x < 32) s_counts[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_kfill = 0;
+    if (prefetch) {
+        // the cone's inputs (whole tile records of every level) on their way into L2 before the level chain starts, and
+        // before the previous kernel has even finished: neither the mirror nor the ranges are written by a frame
+        for (uint32_t level = 0; level < n_levels; ++level) {
+            const uint2 r = __ldg(ranges + (size_t)blockIdx.x * n_levels + level);
+            if (r.y <= r.x) continue;
+            const uint32_t t0 = r.x >> 7, t1 = (r.y - 1u) >> 7;
+            const char *rec = reinterpret_cast<const char *>(P.tiles + (size_t)t0 * kTileFloats);
+            const uint32_t lines = (t1 - t0 + 1u) * (uint32_t)(kTileFloats * sizeof(float) / 128u);
+            for (uint32_t i = threadIdx.x; i < lines; i += kBlockThreads)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (size_t)i * 128u));
+        }
+    }
     cudaGridDependencySynchronize();
     __syncthreads();
     auto flush = [&]() {                                       // block-wide; callers synchronise before and after
