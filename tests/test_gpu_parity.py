@@ -714,6 +714,62 @@ def test_count_boards_two_ranks_on_one_gpu(oracle):
             c.close()
 
 
+def test_count_boards_eight_ranks_on_one_gpu(oracle):
+    """Eight contexts of one process as the eight ranks of a node (whole-world shards, 300 counts per rank: more than
+    one pass of the exchange kernel's block): the host enqueues the ranks' frames in a different random order every
+    round, one rank's worlds change half-way, every rank's last table / offsets / totals are checked."""
+    import torch
+    from astre_b200 import multi
+    world, wpr = 8, 300
+    full = scenes.config5(n_worlds=world * wpr, entities_per_world=64)
+    shards = [full.shard(r, world) for r in range(world)]
+    want = np.stack([oracle.frame(s)[2] for s in shards])
+    ctxs = [GpuContext(s.n, max_views=1) for s in shards]
+    streams = [torch.cuda.Stream() for _ in ctxs]
+    rng = np.random.default_rng(11)
+    try:
+        boards = []
+        for c, s, st in zip(ctxs, shards, streams):
+            scenes.load_into(c, s)
+            c.set_stream(st.cuda_stream)
+            boards.append(c.count_board_create(wpr)[1])
+        ex = []
+        for r, (c, st) in enumerate(zip(ctxs, streams)):
+            with torch.cuda.stream(st):
+                ex.append(multi.PeerCountExchange(c, wpr, boards=boards, rank=r, world=world, rank_major=True))
+
+        def check():
+            for r in range(world):
+                table, off, tot = ex[r].last()
+                assert np.array_equal(table, want), (r, np.argwhere(table != want)[:4])
+                h_off, h_tot = gpu.global_offsets(table, r, True)
+                assert np.array_equal(off, h_off) and np.array_equal(tot, h_tot), r
+
+        for k in range(10):
+            if k == 5:
+                s = shards[3]
+                s.pos = (s.pos * np.float32(0.5)).astype(np.float32)
+                ctxs[3].update_trs_range(0, s.n, s.pos, s.rot, s.scale)
+                want[3] = oracle.frame(s)[2]
+            for r in rng.permutation(world):
+                with torch.cuda.stream(streams[r]):
+                    ex[r].before_frame()
+                    ctxs[r].frame(gpu.FRAME_ALL | (gpu.FRAME_GRAPH if k % 2 else 0))
+                    ex[r].after_frame()
+            if k in (4, 5, 9):
+                check()
+        torch.cuda.synchronize()
+        for c in ctxs:
+            assert c.count_board_status() == (10, 0)
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ex[r].close()
+    finally:
+        for c in ctxs:
+            c.set_stream(None)
+            c.close()
+
+
 def test_gather_inside_the_frame(oracle):
     """ASTRE_FRAME_GATHER: the list's world matrices are produced by the frame itself; short lists (<= 4096 keys) arrive
     in host memory with no copy, longer ones need two copies and no launch, lists beyond the gather buffer fall back."""
