@@ -20,6 +20,15 @@ class DrawRun(C.Structure):
     _fields_ = [("first", C.c_uint32), ("count", C.c_uint32), ("world_view", C.c_uint32), ("shader_mesh", C.c_uint32)]
 
 
+class MeshDrawInfo(C.Structure):
+    _fields_ = [("index_count", C.c_uint32), ("first_index", C.c_uint32), ("base_vertex", C.c_int32)]
+
+
+class DrawIndirect(C.Structure):     # OpenGL's DrawElementsIndirectCommand
+    _fields_ = [("count", C.c_uint32), ("instance_count", C.c_uint32), ("first_index", C.c_uint32), ("base_vertex", C.c_int32),
+                ("base_instance", C.c_uint32)]
+
+
 class MeshBounds(C.Structure):
     _fields_ = [("center", C.c_float * 3), ("extent", C.c_float * 3), ("radius", C.c_float), ("reserved", C.c_uint32)]
 
@@ -74,6 +83,9 @@ SIGNATURES = {
     "astre_gpu_read_visible_world": (C.c_int, [_P, C.c_uint64, C.c_uint64, _F]),
     "astre_gpu_read_draw_list": (C.c_int, [_P, _U64, _F, C.c_uint64, _U64]),
     "astre_gpu_read_runs": (C.c_int, [_P, C.POINTER(DrawRun), C.c_uint32, _U32]),
+    "astre_gpu_set_mesh_draw_info": (C.c_int, [_P, C.c_uint32, C.POINTER(MeshDrawInfo)]),
+    "astre_gpu_build_indirect": (C.c_int, [_P, _U32, C.POINTER(_P)]),
+    "astre_gpu_read_indirect": (C.c_int, [_P, C.POINTER(DrawIndirect), C.c_uint32, _U32]),
     "astre_gpu_slot_entity": (C.c_int, [_P, C.c_uint32, _U64]),
     "astre_gpu_device_world": (_P, [_P]),
     "astre_gpu_device_counts": (_P, [_P]),

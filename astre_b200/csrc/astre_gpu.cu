@@ -168,6 +168,12 @@ struct astre_gpu_ctx {
     RunHead *d_heads = nullptr;          // draw-run heads (f2), in list order
     uint32_t cap_heads = 0;
     uint32_t *d_head_counts = nullptr;   // run heads per CTA of k_run_count, then their exclusive scan (+ total)
+    uint64_t list_serial = 0;            // counts every new draw list (frame, deferred sort, debug sort); never wraps
+    uint64_t heads_serial = ~0ull;       // the list the heads were built for
+    uint32_t n_heads = 0;
+    MeshDrawInfo *d_mesh_info = nullptr; // astre_gpu_set_mesh_draw_info
+    uint32_t n_mesh_info = 0, cap_mesh_info = 0;
+    DrawIndirect *d_indirect = nullptr;  // astre_gpu_build_indirect: one command per run (cap_heads of them)
     uint32_t n_prev = 0;                 // slots that existed at the last astre_gpu_snapshot_trs
     uint32_t epoch = 0;                  // host mirror of SortControl::epoch (one step per frame)
     uint32_t last_want_bits = 0;         // bucket-digit width of the last plan by key count (hysteresis)
@@ -667,7 +673,7 @@ void astre_gpu_destroy(astre_gpu_ctx *ctx)
     void *ptrs[] = { ctx->d_tiles, ctx->d_prev, ctx->d_world, ctx->d_basis, ctx->d_bounds,
                      ctx->d_views, ctx->d_keys[0], ctx->d_keys[1], ctx->d_counts, ctx->d_offsets, ctx->d_ctl, ctx->d_sc,
                      ctx->d_lookback, ctx->d_gather, ctx->d_stage, ctx->d_level_slots, ctx->d_cones, ctx->d_bins, ctx->d_chunk_first, ctx->d_heads,
-                     ctx->d_head_counts,
+                     ctx->d_head_counts, ctx->d_mesh_info, ctx->d_indirect,
                      ctx->d_merged_keys, ctx->d_merged_src, ctx->d_splits, ctx->d_tile_start,
                      ctx->d_mcuts, ctx->d_mdims, ctx->d_merge_error };
     for (void *p : ptrs) if (p) dev_free(p);
@@ -1122,6 +1128,7 @@ int astre_gpu_frame(astre_gpu_ctx *ctx, uint32_t stage_flags, void *stream)
 
     // The frame number that tags look-back words lives on the device (k_frame_begin bumps it, so a captured graph
     // needs no per-frame parameter); this mirror advances in step and clears the tagged words when the tag wraps.
+    ++ctx->list_serial;
     ctx->epoch = ctx->epoch + 1;
     if (ctx->epoch >= kEpochWrap) {
         const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;
@@ -1312,6 +1319,7 @@ int astre_gpu_sort(astre_gpu_ctx *ctx, void *stream)
     ctx->last_flags = (ctx->last_flags & ~(uint32_t)ASTRE_FRAME_SORT_LATER) | ASTRE_FRAME_SORT;
     ctx->sort_pending = false;
     ctx->results_cached = false;
+    ++ctx->list_serial;
     CK(cudaEventRecord(ctx->ev_end, s));
     ctx->last_stream = s;
     return ASTRE_OK;
@@ -1383,16 +1391,16 @@ int astre_gpu_interpolate(astre_gpu_ctx *ctx, float alpha, void *stream)
     return ASTRE_OK;
 }
 
-int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, uint32_t *n_out)
+// The run heads of the last frame's sorted list in d_heads (found and ordered on the device); once per frame.
+static int ensure_run_heads(astre_gpu_ctx *ctx, uint32_t *n_heads_out)
 {
-    if (!ctx || !n_out || (cap && !runs)) return ASTRE_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
     if (int rc = cache_results(ctx)) return rc;
     if (!(ctx->last_flags & ASTRE_FRAME_SORT)) return fail(ctx, ASTRE_ERR_STATE, "draw runs need ASTRE_FRAME_SORT");
     if (ctx->h_overflow) return fail(ctx, ASTRE_ERR_CAPACITY, "frame produced %llu keys, capacity is %llu", ctx->h_total, (unsigned long long)ctx->max_keys);
     const uint32_t n = (uint32_t)ctx->h_total;
-    *n_out = 0;
-    if (!n) return ASTRE_OK;
+    *n_heads_out = 0;
+    if (!n) { ctx->n_heads = 0; ctx->heads_serial = ctx->list_serial; return ASTRE_OK; }
+    if (ctx->heads_serial == ctx->list_serial && ctx->d_heads) { *n_heads_out = ctx->n_heads; return ASTRE_OK; }
     const uint32_t n_ctas = (uint32_t)ctx->sm_count * 8u;
     if (!ctx->d_heads) {
         ctx->cap_heads = (uint32_t)std::min<uint64_t>(ctx->max_keys, 1u << 22);
@@ -1413,6 +1421,21 @@ int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, 
     CK(cudaMemcpyAsync(&n_heads, ctx->d_head_counts + n_ctas, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (n_heads > ctx->cap_heads) return fail(ctx, ASTRE_ERR_CAPACITY, "%u draw runs exceed the internal capacity %u", n_heads, ctx->cap_heads);
+    ctx->n_heads = n_heads;
+    ctx->heads_serial = ctx->list_serial;
+    *n_heads_out = n_heads;
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, uint32_t *n_out)
+{
+    if (!ctx || !n_out || (cap && !runs)) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n_heads = 0;
+    *n_out = 0;
+    if (int rc = ensure_run_heads(ctx, &n_heads)) return rc;
+    if (!n_heads) return ASTRE_OK;
+    const uint32_t n = (uint32_t)ctx->h_total;
     std::vector<RunHead> heads(n_heads);
     CK(cudaMemcpy(heads.data(), ctx->d_heads, (size_t)n_heads * sizeof(RunHead), cudaMemcpyDeviceToHost));
     *n_out = n_heads;
@@ -1422,6 +1445,55 @@ int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, 
         runs[i].world_view = (uint32_t)(heads[i].cls >> 19);
         runs[i].shader_mesh = (uint32_t)(heads[i].cls & ((1ull << 19) - 1ull));
     }
+    return ASTRE_OK;
+}
+
+int astre_gpu_set_mesh_draw_info(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre_mesh_draw_info *info)
+{
+    static_assert(sizeof(astre_mesh_draw_info) == sizeof(MeshDrawInfo), "mesh draw records must match");
+    if (!ctx || (n_meshes && !info)) return ctx ? fail(ctx, ASTRE_ERR_INVALID, "info is null") : ASTRE_ERR_INVALID;
+    if (n_meshes > (1u << ASTRE_KEY_MESH_BITS)) return fail(ctx, ASTRE_ERR_INVALID, "at most 2048 meshes (mesh field of the draw key)");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = astre_gpu_sync(ctx)) return rc;
+    if (n_meshes > ctx->cap_mesh_info) {
+        if (ctx->d_mesh_info) CK(dev_free(ctx->d_mesh_info));
+        ctx->d_mesh_info = nullptr; ctx->cap_mesh_info = 0;
+        CK(dev_alloc(&ctx->d_mesh_info, (size_t)n_meshes * sizeof(MeshDrawInfo)));
+        ctx->cap_mesh_info = n_meshes;
+    }
+    if (n_meshes) CK(cudaMemcpy(ctx->d_mesh_info, info, (size_t)n_meshes * sizeof(MeshDrawInfo), cudaMemcpyHostToDevice));
+    ctx->n_mesh_info = n_meshes;
+    return ASTRE_OK;
+}
+
+int astre_gpu_build_indirect(astre_gpu_ctx *ctx, uint32_t *n_out, const void **commands_dev)
+{
+    static_assert(sizeof(astre_draw_indirect) == sizeof(DrawIndirect) && sizeof(DrawIndirect) == 20, "DrawElementsIndirectCommand layout");
+    if (!ctx || !n_out) return ASTRE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t n_heads = 0;
+    *n_out = 0;
+    if (commands_dev) *commands_dev = nullptr;
+    if (int rc = ensure_run_heads(ctx, &n_heads)) return rc;
+    if (!n_heads) return ASTRE_OK;
+    if (!ctx->d_indirect) CK(dev_alloc(&ctx->d_indirect, (size_t)ctx->cap_heads * sizeof(DrawIndirect)));
+    cudaStream_t s = ctx->last_stream;
+    k_indirect_from_runs<<<ceil_div(n_heads, 256u), 256, 0, s>>>(ctx->d_heads, n_heads, (uint32_t)ctx->h_total, ctx->d_mesh_info,
+                                                                 ctx->n_mesh_info, ctx->d_indirect);
+    CK_LAUNCH();
+    *n_out = n_heads;
+    if (commands_dev) *commands_dev = ctx->d_indirect;
+    return ASTRE_OK;
+}
+
+int astre_gpu_read_indirect(astre_gpu_ctx *ctx, astre_draw_indirect *commands, uint32_t cap, uint32_t *n_out)
+{
+    if (!ctx || !n_out || (cap && !commands)) return ASTRE_ERR_INVALID;
+    const void *dev = nullptr;
+    if (int rc = astre_gpu_build_indirect(ctx, n_out, &dev)) return rc;
+    const uint32_t n = std::min(*n_out, cap);
+    if (n) CK(cudaMemcpyAsync(commands, dev, (size_t)n * sizeof(DrawIndirect), cudaMemcpyDeviceToHost, ctx->last_stream));
+    CK(cudaStreamSynchronize(ctx->last_stream));
     return ASTRE_OK;
 }
 
@@ -1533,6 +1605,7 @@ int astre_gpu_debug_sort_keys(astre_gpu_ctx *ctx, const uint64_t *keys, uint64_t
     std::memset(&fp, 0, sizeof fp);
     fp.plan = make_sort_plan(live_mask);
     fp.bp = make_bin_plan(live_mask, std::max<uint32_t>(2u, std::min<uint32_t>(bin_bits, ctx->cap_bin_bits)));
+    ++ctx->list_serial;
     ctx->epoch = ctx->epoch + 1;                             // in step with the device-side frame number (k_frame_begin)
     if (ctx->epoch >= kEpochWrap) {
         const size_t n_sort_tiles = (size_t)((ctx->max_keys + 2048 - 1) / 2048) + 1;

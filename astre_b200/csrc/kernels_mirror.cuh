@@ -219,6 +219,27 @@ k_run_write(const unsigned long long *__restrict__ keys, uint32_t n, uint32_t cl
     }
 }
 
+// f2, one step further: the runs as indirect draw commands that never leave the GPU.  One record per run in the
+// layout of OpenGL's DrawElementsIndirectCommand (glMultiDrawElementsIndirect): the mesh's index range, one instance
+// per key of the run, baseInstance = the run's first position in the sorted list -- which is also the row of the
+// entity's world matrix in the gathered list (ASTRE_FRAME_GATHER), so a vertex shader reads uModel[gl_BaseInstance +
+// gl_InstanceID].  Runs whose mesh has no entry in the table become empty commands (count 0).
+struct MeshDrawInfo { uint32_t index_count, first_index; int32_t base_vertex; };
+struct DrawIndirect { uint32_t count, instance_count, first_index; int32_t base_vertex; uint32_t base_instance; };
+
+__global__ void __launch_bounds__(256)
+k_indirect_from_runs(const RunHead *__restrict__ heads, const uint32_t n_heads, const uint32_t n_keys,
+                     const MeshDrawInfo *__restrict__ info, const uint32_t n_info, DrawIndirect *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_heads) return;
+    const unsigned long long first = heads[i].index, next = i + 1u < n_heads ? heads[i + 1u].index : n_keys;
+    const uint32_t mesh = (uint32_t)(heads[i].cls & 2047ull);
+    DrawIndirect c{0u, (uint32_t)(next - first), 0u, 0, (uint32_t)first};
+    if (mesh < n_info) { c.count = info[mesh].index_count; c.first_index = info[mesh].first_index; c.base_vertex = info[mesh].base_vertex; }
+    out[i] = c;
+}
+
 // 8e: this rank's segment offsets in the global per-view draw lists, on the device.  all_counts is the
 // all-gathered table [world_size][n_views]; the global list is ordered (view, rank, key), so
 // offsets[v] = sum of every view before v over all ranks + sum of view v over the ranks before this one.

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import AstreError, DrawRun, MeshBounds, load_library
+from ._lib import AstreError, DrawIndirect, DrawRun, MeshBounds, MeshDrawInfo, load_library
 
 FRAME_TRANSFORM, FRAME_CULL, FRAME_SORT, FRAME_BASIS, FRAME_SORT_LATER, FRAME_GRAPH, FRAME_GATHER = 1, 2, 4, 8, 16, 32, 64
 FRAME_ALL = 7
@@ -279,6 +279,27 @@ class GpuContext:
         runs = (DrawRun * max(n.value, 1))()
         self._check(self._lib.astre_gpu_read_runs(self._h, runs, n.value, C.byref(n)))
         return np.array([[r.first, r.count, r.world_view, r.shader_mesh] for r in runs[:n.value]], np.uint32).reshape(-1, 4)
+
+    def set_mesh_draw_info(self, info):
+        """info: [n_meshes, 3] = index_count, first_index, base_vertex of every mesh id (the renderer's index ranges)."""
+        info = np.asarray(info, np.int64).reshape(-1, 3)
+        arr = (MeshDrawInfo * max(len(info), 1))(*[MeshDrawInfo(int(a), int(b), int(c)) for a, b, c in info])
+        self._check(self._lib.astre_gpu_set_mesh_draw_info(self._h, len(info), arr))
+
+    def build_indirect(self):
+        """One DrawElementsIndirectCommand per draw run, left on the device -> (n, device pointer)."""
+        n, p = C.c_uint32(), C.c_void_p()
+        self._check(self._lib.astre_gpu_build_indirect(self._h, C.byref(n), C.byref(p)))
+        return int(n.value), p.value
+
+    def read_indirect(self):
+        """The commands on the host: array [n, 5] = count, instance_count, first_index, base_vertex, base_instance."""
+        n = C.c_uint32()
+        self._check(self._lib.astre_gpu_read_indirect(self._h, None, 0, C.byref(n)))
+        cmds = (DrawIndirect * max(n.value, 1))()
+        self._check(self._lib.astre_gpu_read_indirect(self._h, cmds, n.value, C.byref(n)))
+        return np.array([[c.count, c.instance_count, c.first_index, c.base_vertex, c.base_instance] for c in cmds[:n.value]],
+                        np.int64).reshape(-1, 5)
 
     def slot_entity(self, slot):
         e = C.c_uint64()

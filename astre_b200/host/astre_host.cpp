@@ -321,6 +321,15 @@ void GpuVisualSystem::run(float, Frame &frame)
         frame.draw_runs.push_back(Frame::DrawRun{v, (std::uint32_t)(r.first - view_first[v]), r.count,
                                                  (std::size_t)(r.shader_mesh >> 11), (std::size_t)(r.shader_mesh & 2047u)});
     }
+    frame.draw_commands_dev = nullptr;
+    frame.draw_command_count = 0;
+    if (_indirect) check(_ctx, astre_gpu_build_indirect(_ctx, &frame.draw_command_count, &frame.draw_commands_dev), "astre_gpu_build_indirect");
+}
+
+void GpuVisualSystem::setMeshDrawInfo(const std::vector<astre_mesh_draw_info> &info)
+{
+    check(_ctx, astre_gpu_set_mesh_draw_info(_ctx, (std::uint32_t)info.size(), info.data()), "astre_gpu_set_mesh_draw_info");
+    _indirect = !info.empty();
 }
 
 }  // namespace astre::gpu

@@ -108,6 +108,11 @@ struct Frame {
     // glDrawElements per proxy and pass (Pipeline/src/deferred_shading.cpp:115-174).  `first` indexes draw_lists[view].
     struct DrawRun { std::uint32_t view, first, count; std::size_t shader, vertex_buffer; };
     std::vector<DrawRun> draw_runs;
+    // ... and the same runs as GL DrawElementsIndirectCommand records in device memory (draw_commands_dev[i] belongs to
+    // draw_runs[i]; nullptr unless GpuVisualSystem::setMeshDrawInfo was called): what glMultiDrawElementsIndirect
+    // consumes through CUDA-GL interop instead of one glDrawElements per proxy (Render/src/opengl/opengl.cpp:563-670)
+    const void *draw_commands_dev = nullptr;
+    std::uint32_t draw_command_count = 0;
 };
 
 // Dense slot <-> entity table with spawn/despawn and a dirty set: what keeps
@@ -212,9 +217,13 @@ public:
     // rebuilds frame.render_proxies -- for the entities that survive any view only --
     // plus frame.draw_lists.
     void run(float dt, Frame &frame);
+    // Index range of every vertex buffer id (IRenderer's buffers: index count, first index, base vertex): switches on
+    // frame.draw_commands_dev.
+    void setMeshDrawInfo(const std::vector<astre_mesh_draw_info> &info);
 private:
     EntityMirror &_mirror;
     astre_gpu_ctx *_ctx;
+    bool _indirect = false;
 };
 
 }  // namespace astre::gpu

@@ -253,6 +253,21 @@ typedef struct {
     uint32_t shader_mesh;   /* shader << 11 | mesh */
 } astre_draw_run;
 ASTRE_API int astre_gpu_read_runs(astre_gpu_ctx *ctx, astre_draw_run *runs, uint32_t cap, uint32_t *n_out);
+/* f2, one step further: the runs as indirect draw commands that stay on the GPU.  One record per run, in list
+ * order, in the layout of OpenGL's DrawElementsIndirectCommand (glMultiDrawElementsIndirect; the reference issues one
+ * glDrawElements per proxy, Render/src/opengl/opengl.cpp:563-670): count / first_index / base_vertex from the mesh's
+ * entry of astre_gpu_set_mesh_draw_info (the renderer's index ranges per vertex buffer, Render/src/vertex.cpp), one
+ * instance per key of the run, base_instance = the run's first position in the sorted list = the row of its first
+ * entity in the gathered matrices (ASTRE_FRAME_GATHER / astre_gpu_read_draw_list), so a vertex shader reads
+ * uModel[gl_BaseInstance + gl_InstanceID].  A mesh id without an entry gives an empty command (count 0).  The command
+ * of run i belongs to astre_gpu_read_runs' run i (world, view, shader).  *commands_dev: library-owned device buffer
+ * (a GL buffer can alias it through CUDA-GL interop), valid until the next frame; stream-ordered after the frame.
+ * Spec-defined. */
+typedef struct { uint32_t index_count, first_index; int32_t base_vertex; } astre_mesh_draw_info;
+typedef struct { uint32_t count, instance_count, first_index; int32_t base_vertex; uint32_t base_instance; } astre_draw_indirect;
+ASTRE_API int astre_gpu_set_mesh_draw_info(astre_gpu_ctx *ctx, uint32_t n_meshes, const astre_mesh_draw_info *info);
+ASTRE_API int astre_gpu_build_indirect(astre_gpu_ctx *ctx, uint32_t *n_out, const void **commands_dev);
+ASTRE_API int astre_gpu_read_indirect(astre_gpu_ctx *ctx, astre_draw_indirect *commands, uint32_t cap, uint32_t *n_out);
 
 /* Entity id of a slot (the id given at upload). */
 ASTRE_API int astre_gpu_slot_entity(const astre_gpu_ctx *ctx, uint32_t slot, uint64_t *entity_id);

@@ -172,6 +172,25 @@ static void check_draw_runs(World &w, const Frame &frame)
     for (size_t v = 0; v < frame.draw_lists.size(); ++v) EXPECT(covered[v] == frame.draw_lists[v].size());
 }
 
+// f2 on the device: command i of frame.draw_commands_dev belongs to draw_runs[i]
+static void check_draw_commands(World &w, const Frame &frame, const std::vector<astre_mesh_draw_info> &info)
+{
+    EXPECT(frame.draw_commands_dev != nullptr && frame.draw_command_count == frame.draw_runs.size());
+    std::vector<astre_draw_indirect> cmds(frame.draw_command_count);
+    uint32_t n = 0;
+    EXPECT(astre_gpu_read_indirect(w.ctx, cmds.data(), (uint32_t)cmds.size(), &n) == ASTRE_OK && n == cmds.size());
+    std::vector<size_t> view_first(frame.draw_lists.size() + 1, 0);
+    for (size_t v = 0; v < frame.draw_lists.size(); ++v) view_first[v + 1] = view_first[v] + frame.draw_lists[v].size();
+    for (size_t i = 0; i < cmds.size() && i < frame.draw_runs.size(); ++i) {
+        const Frame::DrawRun &r = frame.draw_runs[i];
+        const bool known = r.vertex_buffer < info.size();
+        EXPECT(cmds[i].instance_count == r.count && cmds[i].base_instance == view_first[r.view] + r.first);
+        EXPECT(cmds[i].count == (known ? info[r.vertex_buffer].index_count : 0u));
+        EXPECT(cmds[i].first_index == (known ? info[r.vertex_buffer].first_index : 0u));
+        EXPECT(cmds[i].base_vertex == (known ? info[r.vertex_buffer].base_vertex : 0));
+    }
+}
+
 static void test_level0_like_world()
 {
     World w(64);
@@ -283,6 +302,12 @@ static void test_random_world(uint32_t n)
     check_against_oracle(w, frame);
     check_draw_runs(w, frame);
     EXPECT(frame.draw_runs.size() >= 4 && frame.draw_runs.size() < frame.draw_lists[0].size());
+    EXPECT(frame.draw_commands_dev == nullptr);                     // off until the renderer's index ranges are known
+    const std::vector<astre_mesh_draw_info> info = {{36, 0, 0}, {6, 36, 24}, {96, 42, 28}, {192, 138, 61}, {60, 330, 94}};
+    w.visuals.setMeshDrawInfo(info);
+    w.visuals.run(0.1f, frame);
+    check_draw_runs(w, frame);
+    check_draw_commands(w, frame, info);
     for (uint32_t i = 0; i < n; i += 17) w.mirror.setPosition(1000 + i, Vec3{P(rng), 1.0f, P(rng) - 50.0f});
     for (uint32_t i = 0; i < n; i += 29) w.mirror.despawn(1000 + i);
     w.transforms.run(0.1f);

@@ -354,6 +354,42 @@ def test_draw_runs(oracle):
     assert runs[:, 1].sum() == len(o_keys) and len(runs) <= 5 * 4 * 8
 
 
+def test_indirect_draw_commands(oracle):
+    """f2, on the device: one DrawElementsIndirectCommand per run (mesh index range, instances = keys of the run,
+    base instance = the run's first list position), against numpy on the oracle's keys; the command buffer stays on
+    the GPU (pointer returned), a mesh id beyond the table gives an empty command, and the next frame rebuilds it."""
+    import torch
+    from astre_b200 import multi
+    for s in (scenes.config3(300_000), scenes.config5(n_worlds=300, entities_per_world=256)):
+        info = np.array([[36, 0, 0], [6, 36, 24], [96, 42, 28], [192, 138, 61], [60, 330, 94], [240, 390, 106]], np.int64)  # meshes 6, 7: no entry
+        with GpuContext(s.n, max_views=s.views_per_world) as ctx:
+            scenes.load_into(ctx, s)
+            ctx.set_mesh_draw_info(info)
+            for frame in range(2):
+                if frame == 1:
+                    s.pos = (s.pos * np.float32(0.5)).astype(np.float32)
+                    ctx.update_trs_range(0, s.n, s.pos, s.rot, s.scale)
+                ctx.frame(gpu.FRAME_ALL | gpu.FRAME_GATHER)
+                n, dev = ctx.build_indirect()
+                cmds = ctx.read_indirect()
+                runs = ctx.read_runs()
+                _, o_keys, _ = oracle.frame(s)
+                world_bits = int(np.ceil(np.log2(s.n_worlds))) if s.n_worlds > 1 else 0
+                cls = o_keys >> np.uint64(40 - world_bits)
+                heads = np.flatnonzero(np.concatenate([[True], cls[1:] != cls[:-1]]))
+                mesh = (cls[heads] & np.uint64(2047)).astype(np.int64)
+                known = mesh < len(info)
+                want = np.zeros((len(heads), 5), np.int64)
+                want[:, 1] = np.diff(np.concatenate([heads, [len(o_keys)]]))
+                want[:, 4] = heads
+                want[known, 0], want[known, 2], want[known, 3] = info[mesh[known], 0], info[mesh[known], 1], info[mesh[known], 2]
+                assert n == len(heads) and dev and np.array_equal(cmds, want)
+                assert (~known).any() and known.any()
+                assert np.array_equal(runs[:, 0], want[:, 4]) and np.array_equal(runs[:, 1], want[:, 1])      # command i belongs to run i
+                on_device = multi.device_view(dev, n * 5, "<i4", torch.device("cuda", 0)).cpu().numpy().reshape(-1, 5)
+                assert np.array_equal(on_device, want.astype(np.int32))
+
+
 def test_interpolate(oracle):
     """f1: interpolateFrame's per-proxy matrix (render.cpp:26-39).  mix / mix and the T*R*S chain are bit-exact; the
     only inexact step is glm::slerp's acos / sin, which the reference takes from the platform's libm: the kernel
