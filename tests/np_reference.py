@@ -187,3 +187,28 @@ def cull_keys(world, mesh, shader, flags, bounds, clip, masks, n_worlds=1, epw=0
             counts[w * F + v] = len(sel)
     keys = np.sort(np.concatenate(keys)) if keys else np.empty(0, np.uint64)
     return keys, counts
+
+
+def draw_runs(keys, world_bits=0):
+    """f2: the sorted key list cut into runs of one class (world, view, shader, mesh = everything above depth and slot).
+    Returns (first position, length, class) per run, in list order."""
+    keys = np.asarray(keys, np.uint64)
+    if len(keys) == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.uint64)
+    cls = keys >> np.uint64(40 - world_bits)
+    heads = np.flatnonzero(np.concatenate([[True], cls[1:] != cls[:-1]]))
+    return heads.astype(np.int64), np.diff(np.concatenate([heads, [len(keys)]])).astype(np.int64), cls[heads]
+
+
+def indirect_commands(keys, mesh_info, world_bits=0):
+    """f2 on the device: one GL DrawElementsIndirectCommand per run -> [n, 5] = count, instanceCount, firstIndex,
+    baseVertex, baseInstance.  mesh_info: [n_meshes, 3] = index count, first index, base vertex; a run whose mesh id has
+    no entry draws nothing (count 0)."""
+    first, length, cls = draw_runs(keys, world_bits)
+    mesh_info = np.asarray(mesh_info, np.int64).reshape(-1, 3)
+    mesh = (cls & np.uint64(2047)).astype(np.int64)
+    known = mesh < len(mesh_info)
+    out = np.zeros((len(first), 5), np.int64)
+    out[:, 1], out[:, 4] = length, first
+    out[known, 0], out[known, 2], out[known, 3] = (mesh_info[mesh[known], c] for c in range(3))
+    return out

@@ -3,6 +3,7 @@ world matrices (0 ULP, NaN payloads aside), per-view counts and sorted draw keys
 import numpy as np
 import pytest
 
+import np_reference
 import oracle_lib
 from astre_b200 import AstreError, GpuContext, gpu, scenes
 
@@ -375,16 +376,9 @@ def test_indirect_draw_commands(oracle):
                 runs = ctx.read_runs()
                 _, o_keys, _ = oracle.frame(s)
                 world_bits = int(np.ceil(np.log2(s.n_worlds))) if s.n_worlds > 1 else 0
-                cls = o_keys >> np.uint64(40 - world_bits)
-                heads = np.flatnonzero(np.concatenate([[True], cls[1:] != cls[:-1]]))
-                mesh = (cls[heads] & np.uint64(2047)).astype(np.int64)
-                known = mesh < len(info)
-                want = np.zeros((len(heads), 5), np.int64)
-                want[:, 1] = np.diff(np.concatenate([heads, [len(o_keys)]]))
-                want[:, 4] = heads
-                want[known, 0], want[known, 2], want[known, 3] = info[mesh[known], 0], info[mesh[known], 1], info[mesh[known], 2]
-                assert n == len(heads) and dev and np.array_equal(cmds, want)
-                assert (~known).any() and known.any()
+                want = np_reference.indirect_commands(o_keys, info, world_bits)        # pinned by tests/test_oracle.py
+                assert n == len(want) and dev and np.array_equal(cmds, want)
+                assert (want[:, 0] == 0).any() and (want[:, 0] != 0).any()
                 assert np.array_equal(runs[:, 0], want[:, 4]) and np.array_equal(runs[:, 1], want[:, 1])      # command i belongs to run i
                 on_device = multi.device_view(dev, n * 5, "<i4", torch.device("cuda", 0)).cpu().numpy().reshape(-1, 5)
                 assert np.array_equal(on_device, want.astype(np.int32))

@@ -263,3 +263,24 @@ def test_box_pretest_only_removes_what_lies_outside_the_view_volume(oracle):
         r = b[6] * np.sqrt(max((m[j, :3] ** 2).sum() for j in range(3)))
         t = e + r
         assert np.any(c + t < lo) or np.any(c - t > hi), (hex(int(key)), c, t, lo, hi)
+
+
+def test_draw_runs_and_indirect_commands_hand_derived():
+    """f2 expectation (np_reference.draw_runs / indirect_commands, the checker of the GPU's astre_gpu_read_runs /
+    astre_gpu_build_indirect) on a key list small enough to cut by hand.  Key = view<<59 | shader<<51 | mesh<<40 |
+    depth<<26 | slot."""
+    def key(view, shader, mesh, depth, slot):
+        return (view << 59) | (shader << 51) | (mesh << 40) | (depth << 26) | slot
+    keys = np.array([key(0, 0, 1, 5, 3), key(0, 0, 1, 9, 1), key(0, 0, 4, 2, 7), key(0, 2, 1, 0, 2),
+                     key(1, 0, 1, 1, 3), key(1, 0, 1, 1, 9), key(1, 0, 1, 7, 0), key(1, 0, 9, 0, 4)], np.uint64)
+    assert all(int(a) < int(b) for a, b in zip(keys[:-1], keys[1:]))     # a sorted list, as the frame produces it
+    first, length, cls = npr.draw_runs(keys)
+    assert first.tolist() == [0, 2, 3, 4, 7] and length.tolist() == [2, 1, 1, 3, 1]
+    assert (cls & np.uint64(2047)).tolist() == [1, 4, 1, 1, 9] and (cls >> np.uint64(19)).tolist() == [0, 0, 0, 1, 1]
+    info = [[36, 0, 0], [6, 36, 24], [12, 42, 28], [24, 54, 40], [60, 78, 52]]          # mesh ids 0..4; 9 has no entry
+    assert npr.indirect_commands(keys, info).tolist() == [[6, 2, 36, 24, 0], [60, 1, 78, 52, 2], [6, 1, 36, 24, 3],
+                                                          [6, 3, 36, 24, 4], [0, 1, 0, 0, 7]]
+    assert npr.indirect_commands(keys[:0], info).shape == (0, 5)
+    # batched worlds: the world index sits above the view field and widens the class
+    wk = np.array([(0 << 62) | key(0, 0, 1, 0, 1) >> 2, (1 << 62) | key(0, 0, 1, 0, 1) >> 2], np.uint64)
+    assert npr.draw_runs(wk, world_bits=2)[0].tolist() == [0, 1]
